@@ -1,0 +1,201 @@
+/* ============================================================================
+ * tslam.h - C ABI of libtslam.so, the B200-native dense-mapping backend.
+ *
+ * The reference (xuhao1/TaichiSLAM) has no FFI layer: its callers use the Python
+ * classes DenseTSDF / Octomap / MarchingCubeMesher directly, and those run Taichi
+ * kernels.  This ABI is what a maintainer binds (ctypes) to
+ * replace each Taichi kernel launch; every entry point names the reference
+ * method/kernel it stands in for (paths relative to taichi_slam/mapping/).
+ *
+ * Conventions
+ *  - plain C types only; opaque handles; no exceptions cross the boundary.
+ *  - every call returns TSLAM_OK (0) or a negative TSLAM_E_* code;
+ *    tslam_last_error() gives a thread-local message for the last failure.
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
+ *    ASYNCHRONOUS on that stream unless documented "synchronises".
+ *  - `mem` arguments: TSLAM_MEM_DEVICE = the pointer is device memory on the
+ *    handle's GPU (caller-owned, must stay alive until the stream reaches the
+ *    call); TSLAM_MEM_HOST = host memory, the library copies it to the device
+ *    itself (truly asynchronous only when the host memory is pinned).
+ *  - handles are not thread-safe; distinct handles are independent.
+ *  - voxel indices are signed and centred: valid i in [-N/2, N/2)
+ *    (dense_tsdf.py:90).  Out-of-volume samples are skipped (the reference
+ *    performs an unchecked access there, mapping_common.py:263-266).
+ * ==========================================================================*/
+#ifndef TSLAM_H
+#define TSLAM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSLAM_OK 0
+#define TSLAM_E_INVALID (-1)   /* bad argument                                  */
+#define TSLAM_E_CUDA (-2)      /* CUDA runtime error (see tslam_last_error)     */
+#define TSLAM_E_POOL_FULL (-3) /* voxel-block pool exhausted; samples dropped   */
+#define TSLAM_E_CAPACITY (-4)  /* caller buffer too small; output saturated     */
+#define TSLAM_E_NOGPU (-5)     /* no CUDA device: there is NO CPU fallback      */
+
+#define TSLAM_MEM_DEVICE 0
+#define TSLAM_MEM_HOST 1
+
+#define TSLAM_MAX_BATCH 64 /* frames per integrate launch (larger calls are split) */
+
+const char* tslam_last_error(void);
+int tslam_device_count(void);
+/* ABI version of this header (tests check the library agrees). */
+int tslam_abi_version(void);
+#define TSLAM_ABI_VERSION 1
+
+/* ----------------------------------------------------------------------------
+ * TSDF map  (DenseTSDF, dense_tsdf.py)
+ * --------------------------------------------------------------------------*/
+typedef struct tslam_tsdf tslam_tsdf_t;
+
+typedef struct tslam_tsdf_config {
+  double voxel_scale;        /* dense_tsdf.py:13 voxel_scale                         */
+  int32_t N, Nz;             /* grid edge in voxels, dense_tsdf.py:24-25             */
+  double max_ray_length;     /* dense_tsdf.py:14                                     */
+  double min_ray_length;     /* dense_tsdf.py:14                                     */
+  int32_t internal_voxels;   /* dense_tsdf.py:15                                     */
+  int32_t recast_step;       /* dense_tsdf.py:16                                     */
+  double fx, fy, cx, cy;     /* K_cam_dep[0],[4],[2],[5]  mapping_common.py:33-36    */
+  int32_t is_global_map;     /* dense_tsdf.py:15                                     */
+  double disp_floor, disp_ceiling; /* dense_tsdf.py:16                               */
+  int32_t max_submaps;       /* dense_tsdf.py:15 max_submap_num                      */
+  int32_t max_blocks;        /* capacity of the 16^3 voxel-block pool (0 = derive)   */
+  int32_t max_image_pixels;  /* largest h*w a depth frame may have (0 = 640*480)     */
+  int32_t max_points;        /* largest point cloud for integrate_points (0 = 1<<20) */
+} tslam_tsdf_config_t;
+
+/* DenseTSDF.__init__ / initialize_fields (dense_tsdf.py:13-118). */
+int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** out);
+int tslam_tsdf_destroy(tslam_tsdf_t* m);
+/* DenseTSDF.reset(): B.parent().deactivate_all() (dense_tsdf.py:309-310). */
+int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream);
+/* BaseMap.set_dep_camera_intrinsic (mapping_common.py:25-26). */
+int tslam_tsdf_set_intrinsics(tslam_tsdf_t* m, double fx, double fy, double cx, double cy);
+/* BaseMap.set_base_pose_submap_kernel (mapping_common.py:126-131): pose table row s. */
+int tslam_tsdf_set_submap_pose(tslam_tsdf_t* m, int32_t s, const float* R9, const float* T3);
+
+/* DenseTSDF.recast_depth_to_map -> recast_depth_to_map_kernel (dense_tsdf.py:162-165,
+ * :188-214) for a batch of n_frames frames.  depth: uint16 [n_frames,h,w] millimetres;
+ * R9s/T3s: HOST arrays [n_frames,9]/[n_frames,3] = input_R/input_T after set_pose's
+ * convert_by_base + f32 cast (mapping_common.py:149-156); submap_ids: HOST int32
+ * [n_frames] (active_submap_id per frame) or NULL for all-zero.
+ * flags: TSLAM_F_COMMIT applies the pending weighted averages before returning
+ * control to the stream (otherwise they stay pending until tslam_tsdf_commit or any
+ * reader).  The per-frame bucket grid (PCLroot.deactivate_all, :163) is implicit. */
+#define TSLAM_F_COMMIT 1
+int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
+                               const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream);
+/* DenseTSDF.recast_pcl_to_map -> recast_pcl_to_map_kernel (dense_tsdf.py:157-160, :167-186).
+ * xyz: float32 [n,3]. */
+int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
+                                int32_t submap, int flags, void* stream);
+/* Apply pending per-voxel weighted averages: T' = (T*W + sum w*d)/(W + sum w),
+ * W' = min(W + sum w, Wmax=1000)  (dense_tsdf.py:264-267 applied once per voxel). */
+int tslam_tsdf_commit(tslam_tsdf_t* m, void* stream);
+
+/* DenseTSDF.count_active (dense_tsdf.py:412-423).  Synchronises. */
+int tslam_tsdf_count_active(tslam_tsdf_t* m, int32_t submap, int64_t* n_out);
+/* DenseTSDF.to_numpy (dense_tsdf.py:425-440): observed voxels of `submap` into
+ * caller DEVICE arrays idx int32[cap,3], tsdf f32[cap], w f32[cap], occ int8[cap]
+ * (row order unspecified, like the reference's atomic counter).  *n_out = demand.
+ * Synchronises.  Returns TSLAM_E_CAPACITY (outputs saturated) when demand > cap. */
+int tslam_tsdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* tsdf, float* w, int8_t* occ,
+                      int64_t* n_out, void* stream);
+/* DenseTSDF.load_numpy (dense_tsdf.py:442-454): DEVICE arrays, n rows. */
+int tslam_tsdf_scatter(tslam_tsdf_t* m, int32_t submap, int64_t n, const int32_t* idx, const float* tsdf, const float* w,
+                       const int8_t* occ, void* stream);
+/* DenseTSDF.fuse_submaps -> reset() + fuse_submaps_kernel (dense_tsdf.py:272-318):
+ * trilinear splat (7 corners, :300) of every observed voxel of every submap of `src`
+ * into submap 0 of `dst`, using dst's pose table.  No Wmax clamp (:274-278). */
+int tslam_tsdf_fuse(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* stream);
+/* cvt_TSDF_surface_to_voxels_kernel (dense_tsdf.py:339-365): append |TSDF|<1.8*vs
+ * voxels of `submap` to xyz/rgb f32[cap,3] (DEVICE) starting at *count_dev (DEVICE
+ * int32 counter, incremented; entries beyond cap are counted but not written). */
+int tslam_tsdf_extract_surface(tslam_tsdf_t* m, int32_t submap, int64_t cap, float* xyz, float* rgb, int32_t* count_dev,
+                               void* stream);
+/* cvt_TSDF_to_voxels_slice_kernel (dense_tsdf.py:367-385). val = TSDF value. */
+int tslam_tsdf_extract_slice(tslam_tsdf_t* m, int32_t submap, float z, float dz, int64_t cap, float* xyz, float* val,
+                             float* rgb, int32_t* count_dev, void* stream);
+/* Counters since the last clear: [0] sampled pixels, [1] valid pixels (range filter),
+ * [2] rays (live buckets), [3] voxel updates applied, [4] out-of-volume samples,
+ * [5] allocated voxel blocks, [6] device error flags, [7] integrate launches.
+ * Synchronises. */
+int tslam_tsdf_get_stats(tslam_tsdf_t* m, int64_t* out8, int clear);
+/* Block until all work enqueued on `stream` for this map is done and report a
+ * deferred device error (TSLAM_E_POOL_FULL) if one was raised. */
+int tslam_tsdf_sync(tslam_tsdf_t* m, void* stream);
+/* Kernels launched by this handle since creation (bench.py `gpu_launches`). */
+int64_t tslam_tsdf_launch_count(tslam_tsdf_t* m);
+/* CUDA-event timing of the integrate kernels, recorded on the launching stream when
+ * profiling is on (ring of the last 512 integrate launches).  tslam_tsdf_kernel_ms writes
+ * ms3[3*i+{0,1,2}] = bucket / ray-march / commit kernel time of the i-th most recent launch,
+ * i < min(n, recorded); *n_out = rows written.  Synchronises. */
+int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on);
+int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out);
+
+/* ----------------------------------------------------------------------------
+ * Marching cubes  (MarchingCubeMesher, marching_cube_mesher.py)
+ * --------------------------------------------------------------------------*/
+/* generate_mesh_kernel (marching_cube_mesher.py:127-187): two-pass (count, scan,
+ * emit) marching cubes over every active block of `m`.  verts/normals: DEVICE
+ * f32 [3*cap_tri,3]; *n_tri_out = true triangle demand (host).  Synchronises. */
+int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float tsdf_surface_thres, int64_t cap_tri, float* verts,
+                      float* normals, int64_t* n_tri_out, void* stream);
+
+/* ----------------------------------------------------------------------------
+ * ESDF  (DenseSDF.propogate_esdf semantics, dense_esdf.py:228-333)
+ * --------------------------------------------------------------------------*/
+/* Converged 26-neighbour signed distance wavefront over the observed voxels of
+ * `submap`.  *n_sweeps_out (host, optional) = global sweeps until no change. */
+int tslam_esdf_update(tslam_tsdf_t* m, int32_t submap, int32_t* n_sweeps_out, void* stream);
+/* ESDF of observed voxels: idx int32[cap,3], esdf f32[cap] (DEVICE). Synchronises. */
+int tslam_esdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* esdf, int64_t* n_out,
+                      void* stream);
+
+/* ----------------------------------------------------------------------------
+ * Octomap = per-voxel hit counter  (Octomap, taichi_octomap.py)
+ * --------------------------------------------------------------------------*/
+typedef struct tslam_octo tslam_octo_t;
+typedef struct tslam_octo_config {
+  double voxel_scale;       /* the CONSTRUCTOR's voxel_scale (mapping_common.py:22-23) */
+  int32_t N, Nz, K;         /* taichi_octomap.py:19-27                                 */
+  double max_ray_length, min_ray_length;
+  int32_t recast_step;
+  double fx, fy, cx, cy;
+  int32_t min_occupy_thres; /* taichi_octomap.py:30,86-88                              */
+  int32_t max_submaps;
+  int32_t max_blocks;       /* capacity of the 8^3 counter-block pool (0 = derive)     */
+  int32_t max_image_pixels;
+  int32_t max_points;
+} tslam_octo_config_t;
+
+int tslam_octo_create(const tslam_octo_config_t* cfg, tslam_octo_t** out);
+int tslam_octo_destroy(tslam_octo_t* m);
+int tslam_octo_reset(tslam_octo_t* m, void* stream); /* root.deactivate_all() taichi_octomap.py:210-211 */
+int tslam_octo_set_submap_pose(tslam_octo_t* m, int32_t s, const float* R9, const float* T3);
+/* recast_pcl_to_map_kernel (taichi_octomap.py:134-145): occupy[round((R p + T)/vs)] += 1. */
+int tslam_octo_integrate_points(tslam_octo_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
+                                int32_t submap, void* stream);
+/* recast_depth_to_map_kernel (taichi_octomap.py:147-169). */
+int tslam_octo_integrate_depth(tslam_octo_t* m, const uint16_t* depth, int mem, int32_t h, int32_t w, const float* R9,
+                               const float* T3, int32_t submap, void* stream);
+/* every (i,j,k,count>0) of `submap`: idx int32[cap,3], count uint32[cap] (DEVICE). Synchronises. */
+int tslam_octo_gather(tslam_octo_t* m, int32_t submap, int64_t cap, int32_t* idx, uint32_t* count, int64_t* n_out,
+                      void* stream);
+/* cvt_occupy_to_voxels(level) / cvt_occupy_voxels_to (taichi_octomap.py:90-114): append to
+ * xyz f32[cap,3] at *count_dev. */
+int tslam_octo_extract(tslam_octo_t* m, int32_t submap, int32_t level, int64_t cap, float* xyz, int32_t* count_dev,
+                       void* stream);
+/* fuse_submaps_kernel (taichi_octomap.py:171-189) after reset(). */
+int tslam_octo_fuse(tslam_octo_t* dst, tslam_octo_t* src, void* stream);
+int tslam_octo_sync(tslam_octo_t* m, void* stream);
+int64_t tslam_octo_launch_count(tslam_octo_t* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSLAM_H */

@@ -1,0 +1,267 @@
+// Internal structures of libtslam.so (sm_100a).  Not part of the ABI.
+//
+// HBM layout of a TSDF map (replaces Taichi's pointer->dense SNode tree,
+// dense_tsdf.py:108-118):
+//   * one open-addressing hash table  slot -> (key40 | block24)   8 B/slot
+//   * a pool of 16^3-voxel blocks stored as per-field PLANES (SoA across the pool,
+//     4096 consecutive voxels of one block are contiguous in every plane):
+//         acc  float2[4096]  pending (sum w*d, sum w) of not-yet-committed frames
+//         tw   float2[4096]  committed (TSDF, W_TSDF)   (f16 x2 in the reference)
+//         obs  u8[4096]      TSDF_observed
+//         occ  i8[4096]      occupy
+//     A voxel update of the ray-march kernel is ONE 8-byte vector reduction
+//     (REDG.E.ADD.F32x2) into `acc`; whole blocks are streamed by the commit /
+//     marching-cubes / export kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tslam.h"
+
+#define TS_B 16
+#define TS_B3 4096
+#define TS_BSHIFT 4
+#define TS_BMASK 15
+
+// packed hash word:  [63:24] key (s:10 | bx:10 | by:10 | bz:10), [23:0] block index
+#define TS_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define TS_IDX_MASK 0xFFFFFFull
+#define TS_IDX_PENDING 0xFFFFFEull
+#define TS_IDX_OVERFLOW 0xFFFFFDull
+#define TS_MAX_BLOCKS 0xFFFFF0
+
+#define TS_ERR_POOL_FULL 1
+#define TS_ERR_TABLE_FULL 2
+#define TS_ERR_RAYLIST_FULL 4
+#define TS_PROF_RING 512
+
+struct TsGrid {
+  unsigned long long* table;  // hash words
+  uint32_t table_mask;        // capacity-1 (power of two)
+  int max_blocks;
+  int* n_blocks;              // device allocation counter
+  unsigned long long* block_key;  // [max_blocks] reverse map (key40)
+  float2* acc;                // [max_blocks*4096]
+  float2* tw;                 // [max_blocks*4096]
+  uint8_t* obs;               // [max_blocks*4096]
+  int8_t* occ;                // [max_blocks*4096]
+  float* esdf;                // [max_blocks*4096] (allocated lazily by the ESDF path)
+  int* dirty_flag;            // [max_blocks]
+  int* dirty_list;            // [max_blocks]
+  int* n_dirty;
+  int* err;                   // device error flags
+  int hN, hNz, N, Nz;         // bounds: i in [-hN, N-hN)
+};
+
+__host__ __device__ __forceinline__ unsigned long long ts_pack_key(int s, int bx, int by, int bz) {
+  return ((unsigned long long)(s & 1023) << 30) | ((unsigned long long)((bx + 512) & 1023) << 20) |
+         ((unsigned long long)((by + 512) & 1023) << 10) | (unsigned long long)((bz + 512) & 1023);
+}
+__host__ __device__ __forceinline__ void ts_unpack_key(unsigned long long k, int& s, int& bx, int& by, int& bz) {
+  s = (int)((k >> 30) & 1023);
+  bx = (int)((k >> 20) & 1023) - 512;
+  by = (int)((k >> 10) & 1023) - 512;
+  bz = (int)(k & 1023) - 512;
+}
+__device__ __forceinline__ uint32_t ts_hash(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+template <class G>
+__device__ __forceinline__ bool ts_in_bounds(const G& g, int i, int j, int k) {
+  return i >= -g.hN && i < g.N - g.hN && j >= -g.hN && j < g.N - g.hN && k >= -g.hNz && k < g.Nz - g.hNz;
+}
+__device__ __forceinline__ int ts_voxel_off(int i, int j, int k) {
+  return (((i & TS_BMASK) << TS_BSHIFT) | (j & TS_BMASK)) << TS_BSHIFT | (k & TS_BMASK);
+}
+__device__ __forceinline__ unsigned long long ts_ld_volatile(const unsigned long long* p) {
+  return *(const volatile unsigned long long*)p;
+}
+
+// read-only lookup: block index or -1   (G = TsGrid or OcGrid)
+template <class G>
+__device__ __forceinline__ int ts_find(const G& g, unsigned long long key) {
+  uint32_t slot = ts_hash(key) & g.table_mask;
+  for (uint32_t probe = 0; probe <= g.table_mask; ++probe) {
+    unsigned long long cur = ts_ld_volatile(&g.table[slot]);
+    if (cur == TS_EMPTY) return -1;
+    if ((cur >> 24) == key) {
+      unsigned idx = (unsigned)(cur & TS_IDX_MASK);
+      return (idx >= TS_IDX_OVERFLOW) ? -1 : (int)idx;
+    }
+    slot = (slot + 1) & g.table_mask;
+  }
+  return -1;
+}
+
+// lookup, activating a zero-filled block on miss (Taichi "write activates").
+// Returns -1 when the pool is exhausted (error flag raised, sample dropped).
+template <class G>
+__device__ __forceinline__ int ts_get_or_alloc(const G& g, unsigned long long key) {
+  uint32_t slot = ts_hash(key) & g.table_mask;
+  for (uint32_t probe = 0; probe <= g.table_mask; ++probe) {
+    unsigned long long cur = ts_ld_volatile(&g.table[slot]);
+    if (cur == TS_EMPTY) {
+      unsigned long long prev = atomicCAS(&g.table[slot], TS_EMPTY, (key << 24) | TS_IDX_PENDING);
+      if (prev == TS_EMPTY) {
+        int idx = atomicAdd(g.n_blocks, 1);
+        unsigned long long word;
+        if (idx >= g.max_blocks) {
+          atomicSub(g.n_blocks, 1);
+          atomicOr(g.err, TS_ERR_POOL_FULL);
+          word = (key << 24) | TS_IDX_OVERFLOW;
+          idx = -1;
+        } else {
+          g.block_key[idx] = key;
+          word = (key << 24) | (unsigned long long)idx;
+        }
+        __threadfence();
+        atomicExch(&g.table[slot], word);
+        return idx;
+      }
+      cur = prev;
+    }
+    if ((cur >> 24) == key) {
+      while ((cur & TS_IDX_MASK) == TS_IDX_PENDING) {
+        __nanosleep(32);
+        cur = ts_ld_volatile(&g.table[slot]);
+      }
+      unsigned idx = (unsigned)(cur & TS_IDX_MASK);
+      return (idx >= TS_IDX_OVERFLOW) ? -1 : (int)idx;
+    }
+    slot = (slot + 1) & g.table_mask;
+  }
+  atomicOr(g.err, TS_ERR_TABLE_FULL);
+  return -1;
+}
+
+__device__ __forceinline__ void ts_mark_dirty(const TsGrid& g, int blk) {
+  if (*(volatile int*)&g.dirty_flag[blk] == 0) {
+    if (atomicExch(&g.dirty_flag[blk], 1) == 0) {
+      int p = atomicAdd(g.n_dirty, 1);
+      g.dirty_list[p] = blk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-frame parameters of one integrate launch, passed BY VALUE as a
+// __grid_constant__ kernel parameter (no H2D copy, no lifetime hazards)
+// ---------------------------------------------------------------------------
+struct TsFrame {
+  float R[9];
+  float T[3];
+  int submap;
+};
+struct TsBatch {
+  TsFrame f[TSLAM_MAX_BATCH];  // 64 * 52 B = 3328 B
+};
+
+struct TsIntrin {
+  float fx, fy, cx, cy;
+  float dmin_mm, dmax_mm;  // f32(min_ray*1000), f32(max_ray*1000)
+  float vs;
+  float max_steps;         // f32(max_ray_length / voxel_scale)
+  float max_ray;           // f32(max_ray_length)
+  int internal_voxels;
+  int step;
+};
+
+// per-frame bucket entry (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z),
+// exact fixed-point sums (2^-20 m).  64-byte stride = two 32-byte sectors.
+struct __align__(64) TsBucket {
+  unsigned long long key;  // packed (bx,by,bz)+1, 0 = empty
+  long long sx, sy, sz, sd;
+  int cnt;
+  int pad[5];
+};
+
+struct TsCounters {  // device-side statistics (tslam_tsdf_get_stats)
+  unsigned long long n_px, n_valid, n_rays, n_updates, n_oob;
+};
+
+// host-side handle
+struct tslam_tsdf {
+  tslam_tsdf_config_t cfg;
+  int device;
+  TsGrid g;
+  TsIntrin in;
+  size_t table_cap;
+  // integrate workspace
+  TsBucket* buckets;   // [TSLAM_MAX_BATCH * bucket_cap]
+  uint32_t bucket_cap; // power of two
+  uint32_t* ray_list;  // [TSLAM_MAX_BATCH * max_rays_per_frame]
+  uint32_t ray_list_cap;
+  int* n_rays;         // device counter
+  uint16_t* depth_stage;  // device staging for host depth input [TSLAM_MAX_BATCH * max_image_pixels]
+  float* points_stage;    // device staging for host point clouds
+  TsCounters* counters;
+  float* pose_R;       // device pose table [max_submaps*9]
+  float* pose_T;       // [max_submaps*3]
+  float* colormap;     // device jet LUT [1024*3]
+  int* scratch_i;      // small device scratch (counters for gather etc.)
+  long long launches;
+  int n_integrate_calls;
+  int profiling;
+  cudaEvent_t* ev;          // profiling ring: TS_PROF_RING launches x 4 events (created lazily)
+  long long prof_launches;  // integrate launches recorded since profiling was switched on
+  int sm_count;
+  bool clamp_on_commit;
+};
+
+// ---------------------------------------------------------------------------
+// Octomap: hash grid of 8^3 blocks of u32 hit counters (taichi_octomap.py:63-84
+// builds a K-ary pointer tree with one allocation per leaf instead)
+// ---------------------------------------------------------------------------
+#define OC_B 8
+#define OC_B3 512
+#define OC_BSHIFT 3
+#define OC_BMASK 7
+struct OcGrid {
+  unsigned long long* table;
+  uint32_t table_mask;
+  int max_blocks;
+  int* n_blocks;
+  unsigned long long* block_key;
+  unsigned int* cnt;  // [max_blocks*512]
+  int* err;
+  int hN, hNz, N, Nz;
+};
+__device__ __forceinline__ int oc_voxel_off(int i, int j, int k) {
+  return (((i & OC_BMASK) << OC_BSHIFT) | (j & OC_BMASK)) << OC_BSHIFT | (k & OC_BMASK);
+}
+struct tslam_octo {
+  tslam_octo_config_t cfg;
+  OcGrid g;
+  TsIntrin in;
+  size_t table_cap;
+  uint16_t* depth_stage;
+  float* points_stage;
+  float* pose_R;
+  float* pose_T;
+  int* scratch_i;
+  long long launches;
+  int sm_count;
+};
+
+// error plumbing (tslam_tsdf.cu)
+void ts_set_error(const char* fmt, ...);
+int ts_cuda_fail(cudaError_t e, const char* what);
+#define TS_CUDA(x)                                    \
+  do {                                                \
+    cudaError_t _e = (x);                             \
+    if (_e != cudaSuccess) return ts_cuda_fail(_e, #x); \
+  } while (0)
+#define TS_LAUNCH_CHECK(m)                                              \
+  do {                                                                  \
+    (m)->launches++;                                                    \
+    cudaError_t _e = cudaGetLastError();                                \
+    if (_e != cudaSuccess) return ts_cuda_fail(_e, "kernel launch");    \
+  } while (0)
+
+// shared across translation units
+int ts_flush_pending(tslam_tsdf* m, cudaStream_t st);   // commit if anything is pending
+int ts_check_deferred(tslam_tsdf* m);                    // read + translate device error flags (synchronises)

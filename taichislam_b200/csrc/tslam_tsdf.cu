@@ -1,0 +1,947 @@
+// libtslam.so - TSDF map: hash grid of 16^3 voxel blocks, depth / point-cloud
+// integration (bucket -> ray-march -> commit), I/O and export kernels.  sm_100a.
+//
+// Reference semantics: taichi_slam/mapping/dense_tsdf.py (cited per kernel).
+// Compiled with -fmad=false: the index-forming arithmetic must round exactly like
+// the strict-IEEE statement of the reference source (voxel indices are compared
+// bit-for-bit by the parity tests).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <cuda_fp16.h>
+#include "tslam_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void ts_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int ts_cuda_fail(cudaError_t e, const char* what) {
+  ts_set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TSLAM_E_NOGPU : TSLAM_E_CUDA;
+}
+extern "C" const char* tslam_last_error(void) { return g_err; }
+extern "C" int tslam_abi_version(void) { return TSLAM_ABI_VERSION; }
+extern "C" int tslam_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+#define WMAX 1000.0f          // dense_tsdf.py:8
+#define FIXQ 1048576.0f       // 2^20: fixed-point quantum of the per-frame bucket sums
+#define FIXQ_D 1048576.0
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int iroundf(float x) { return (int)roundf(x); }  // ti.round(x, i32) mapping_common.py:263-266
+__device__ __forceinline__ float sgnf(float v) { return (float)((0.0f < v) - (v < 0.0f)); }  // mapping_common.py:5-7
+
+__device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz) {
+  return ((((unsigned long long)(bx + (1 << 20)) << 42) | ((unsigned long long)(by + (1 << 20)) << 21) |
+           (unsigned long long)(bz + (1 << 20))) + 1ull);
+}
+
+__device__ __forceinline__ void red_add_f32x2(float2* addr, float a, float b) {
+  // one 8-byte vector reduction: REDG.E.ADD.F32x2 (sm_90+)
+  atomicAdd(addr, make_float2(a, b));
+}
+
+// accumulate one unprojected point into its frame's bucket table.
+// process_point (dense_tsdf.py:227-234) with exact fixed-point sums.
+__device__ __forceinline__ void bucket_accumulate(TsBucket* tab, uint32_t cap_mask, uint32_t tab_base, float px, float py,
+                                                  float pz, float dep, float vs, uint32_t* ray_list, int* n_rays,
+                                                  uint32_t ray_cap, int* err) {
+  int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
+  unsigned long long key = bucket_key(bx, by, bz);
+  uint32_t h = ts_hash(key) & cap_mask;
+  TsBucket* b = nullptr;
+  for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
+    TsBucket* c = &tab[h];
+    unsigned long long cur = ts_ld_volatile(&c->key);
+    if (cur == 0ull) {
+      unsigned long long prev = atomicCAS(&c->key, 0ull, key);
+      if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
+        uint32_t p = (uint32_t)atomicAdd(n_rays, 1);
+        if (p < ray_cap) ray_list[p] = tab_base + h; else atomicOr(err, TS_ERR_RAYLIST_FULL);
+        b = c;
+        break;
+      }
+      cur = prev;
+    }
+    if (cur == key) { b = c; break; }
+    h = (h + 1) & cap_mask;
+  }
+  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return; }
+  atomicAdd(&b->cnt, 1);
+  atomicAdd((unsigned long long*)&b->sx, (unsigned long long)__float2ll_rn(px * FIXQ));
+  atomicAdd((unsigned long long*)&b->sy, (unsigned long long)__float2ll_rn(py * FIXQ));
+  atomicAdd((unsigned long long*)&b->sz, (unsigned long long)__float2ll_rn(pz * FIXQ));
+  atomicAdd((unsigned long long*)&b->sd, (unsigned long long)__float2ll_rn(dep * FIXQ));
+}
+
+// ---------------------------------------------------------------------------
+// K1a: depth frames -> per-frame buckets.
+// recast_depth_to_map_kernel phase 1 (dense_tsdf.py:188-213) + unproject_point_dep
+// (mapping_common.py:31-41).  One thread per SAMPLED pixel (the reference walks a
+// row per thread, :192-194), blockIdx.y = frame of the batch.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int h, int w, int hh, int ww,
+                                                       const __grid_constant__ TsBatch batch, TsIntrin in,
+                                                       TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
+                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
+  const int f = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  if (t < hh * ww) {
+    const int jj = t / ww, ii = t - jj * ww;
+    const int j = jj * in.step, i = ii * in.step;
+    const uint16_t d = depth[(size_t)f * h * w + (size_t)j * w + i];
+    const float df = (float)d;
+    if (d != 0 && !(df > in.dmax_mm || df < in.dmin_mm)) {  // :196-199
+      valid = true;
+      const float dep = df / 1000.0f;                        // :201
+      const float x = ((float)i - in.cx) * dep / in.fx;     // mapping_common.py:37-40
+      const float y = ((float)j - in.cy) * dep / in.fy;
+      const TsFrame& fr = batch.f[f];
+      const float px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * dep;  // :203 input_R @ pt (rotation only)
+      const float py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * dep;
+      const float pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * dep;
+      bucket_accumulate(buckets + (size_t)f * bucket_cap, bucket_cap - 1, (uint32_t)f * bucket_cap, px, py, pz, dep, in.vs,
+                        ray_list, n_rays, ray_cap, err);
+    }
+  }
+  const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+  if ((threadIdx.x & 31) == 0) {
+    if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
+  }
+}
+
+// K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
+__global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
+                                                        TsIntrin in, TsBucket* buckets, uint32_t bucket_cap,
+                                                        uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
+                                                        int* err) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  if (t < n) {
+    const float x = xyz[3 * (size_t)t], y = xyz[3 * (size_t)t + 1], z = xyz[3 * (size_t)t + 2];
+    const TsFrame& fr = batch.f[0];
+    const float px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * z;  // :175
+    const float py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * z;
+    const float pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * z;
+    const float len = sqrtf((px * px + py * py) + pz * pz);       // :176
+    if (len < in.max_ray) {                                       // :177
+      valid = true;
+      bucket_accumulate(buckets, bucket_cap - 1, 0u, px, py, pz, len, in.vs, ray_list, n_rays, ray_cap, err);  // :185
+    }
+  }
+  const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+  if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
+  if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
+}
+
+// ---------------------------------------------------------------------------
+// K2: ray march.  process_new_pcl (dense_tsdf.py:236-270).  One thread per live
+// bucket (= ray) of any frame of the batch; every step issues one 8-byte vector
+// reduction (w*d, w) into the block's `acc` plane - the reference's racy RMW
+// (:264-267) becomes an order-independent sum that k_commit folds into (TSDF, W).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_raymarch(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
+                                                   TsBucket* buckets, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
+                                                   const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
+  const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
+  const float vs = in.vs;
+  unsigned int my_updates = 0, my_oob = 0, my_rays = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += gridDim.x * blockDim.x) {
+    const uint32_t id = ray_list[r];
+    const uint32_t f = id >> bucket_shift;
+    TsBucket* bk = &buckets[id];
+    const int cnt = bk->cnt;
+    const long long sx = bk->sx, sy = bk->sy, sz = bk->sz, sd = bk->sd;
+    {  // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
+      uint4 z4 = make_uint4(0, 0, 0, 0);
+      uint4* q = reinterpret_cast<uint4*>(bk);
+      q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
+    }
+    if (cnt <= 0) continue;  // :240
+    my_rays++;
+    const TsFrame& fr = batch.f[f];
+    const int s = fr.submap;
+    const double den = (double)cnt * FIXQ_D;
+    const float mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
+    const float my = (float)((double)sy / den);
+    const float mz = (float)((double)sz / den);
+    const float zc = (float)((double)sd / den);  // z = new_pcl_z/c (:247)
+    const float L = sqrtf((mx * mx + my * my) + mz * mz);  // :244
+    if (!(L > 0.0f)) continue;
+    const float ux = mx / L, uy = my / L, uz = mz / L;  // :245
+    const float Tx = fr.T[0], Ty = fr.T[1], Tz = fr.T[2];
+    const float Px = mx + Tx, Py = my + Ty, Pz = mz + Tz;  // :246
+    unsigned long long cur_key = TS_EMPTY;
+    int cur_blk = -1;
+    {  // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
+      const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
+      if (ts_in_bounds(g, oi, oj, ok)) {
+        cur_key = ts_pack_key(s, oi >> TS_BSHIFT, oj >> TS_BSHIFT, ok >> TS_BSHIFT);
+        cur_blk = ts_get_or_alloc(g, cur_key);
+        if (cur_blk >= 0) {
+          g.occ[(size_t)cur_blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
+          ts_mark_dirty(g, cur_blk);  // touched blocks are listed even when only `occupy` changed
+        }
+      }
+    }
+    const int n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
+    const float wgt = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
+    float jf = 0.0f;
+    for (int it = 0; it < n; ++it) {
+      jf += 1.0f;  // :252
+      const float x = (ux * jf) * vs + Tx, y = (uy * jf) * vs + Ty, z = (uz * jf) * vs + Tz;  // :253
+      const int xi = iroundf(x / vs), yi = iroundf(y / vs), zi = iroundf(z / vs);           // :254
+      const float vx = Px - x, vy = Py - y, vz = Pz - z;                                      // :258
+      const float d = sqrtf((vx * vx + vy * vy) + vz * vz);                                  // :259
+      const float ds = d * sgnf((vx * mx + vy * my) + vz * mz);                              // :260
+      if (!ts_in_bounds(g, xi, yi, zi)) { my_oob++; continue; }
+      const unsigned long long key = ts_pack_key(s, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
+      if (key != cur_key) {
+        cur_key = key;
+        cur_blk = ts_get_or_alloc(g, key);
+        if (cur_blk >= 0) ts_mark_dirty(g, cur_blk);
+      }
+      if (cur_blk < 0) continue;  // pool exhausted (error flag raised)
+      red_add_f32x2(&g.acc[(size_t)cur_blk * TS_B3 + ts_voxel_off(xi, yi, zi)], wgt * ds, wgt);  // :264,:267
+      my_updates++;
+    }
+  }
+  // statistics: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
+    my_oob += __shfl_xor_sync(0xffffffffu, my_oob, o);
+    my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (my_updates) atomicAdd(&ctr->n_updates, (unsigned long long)my_updates);
+    if (my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
+    if (my_rays) atomicAdd(&ctr->n_rays, (unsigned long long)my_rays);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: commit.  Folds the pending (sum w*d, sum w) of every dirty block into
+// (TSDF, W_TSDF):  T' = (T*W + A)/(W + B), W' = min(W + B, Wmax), observed = 1
+// (dense_tsdf.py:264-267 applied once per voxel per batch).  One CTA per block,
+// fully coalesced float2 streams.  clamp=0 is the fusion variant (:274-278).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit(TsGrid g, int clamp, int fused_obs) {
+  const int nd = *g.n_dirty;
+  for (int q = blockIdx.x; q < nd; q += gridDim.x) {
+    const int blk = g.dirty_list[q];
+    float2* acc = g.acc + (size_t)blk * TS_B3;
+    float2* tw = g.tw + (size_t)blk * TS_B3;
+    uint8_t* obs = g.obs + (size_t)blk * TS_B3;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      const float2 a = acc[v];
+      // integrate: a voxel is touched iff sum w > 0.  fusion: also voxels whose observed
+      // flag was raised by a zero-weight corner (0/0 = NaN is reference behaviour).
+      const bool touched = fused_obs ? (a.y != 0.0f || a.x != 0.0f || obs[v] == 2) : (a.y > 0.0f);
+      if (touched) {
+        const float2 o = tw[v];
+        const float wn = o.y + a.y;
+        float2 r;
+        r.x = (o.x * o.y + a.x) / wn;
+        r.y = clamp ? fminf(wn, WMAX) : wn;
+        tw[v] = r;
+        obs[v] = 1;
+        acc[v] = make_float2(0.0f, 0.0f);
+      }
+    }
+    if (threadIdx.x == 0) g.dirty_flag[blk] = 0;
+  }
+}
+__global__ void k_reset_counters(int* a, int* b) {
+  if (a) *a = 0;
+  if (b) *b = 0;
+}
+
+// ---------------------------------------------------------------------------
+// host: create / destroy / reset
+// ---------------------------------------------------------------------------
+static size_t next_pow2(size_t v) {
+  size_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static void fill_jet_host(float* cm) {
+  // colormap[i] = matplotlib.cm.jet(i/1024) (mapping_common.py:158-163) = 256-entry LUT of
+  // the piecewise-linear jet segment data, sampled at i//4.
+  static const float r[][2] = {{0, 0}, {0.35f, 0}, {0.66f, 1}, {0.89f, 1}, {1, 0.5f}};
+  static const float gg[][2] = {{0, 0}, {0.125f, 0}, {0.375f, 1}, {0.64f, 1}, {0.91f, 0}, {1, 0}};
+  static const float b[][2] = {{0, 0.5f}, {0.11f, 1}, {0.34f, 1}, {0.65f, 0}, {1, 0}};
+  auto seg = [](const float (*d)[2], int n, float x) {
+    for (int i = 1; i < n; i++)
+      if (x <= d[i][0]) {
+        float t = (x - d[i - 1][0]) / (d[i][0] - d[i - 1][0]);
+        return d[i - 1][1] + t * (d[i][1] - d[i - 1][1]);
+      }
+    return d[n - 1][1];
+  };
+  for (int i = 0; i < 1024; i++) {
+    float x = (float)(i / 4) / 255.0f;
+    cm[3 * i] = seg(r, 5, x);
+    cm[3 * i + 1] = seg(gg, 6, x);
+    cm[3 * i + 2] = seg(b, 5, x);
+  }
+}
+
+static void ts_fill_intrin(tslam_tsdf* m) {
+  const tslam_tsdf_config_t& c = m->cfg;
+  m->in.fx = (float)c.fx; m->in.fy = (float)c.fy; m->in.cx = (float)c.cx; m->in.cy = (float)c.cy;
+  m->in.dmin_mm = (float)(c.min_ray_length * 1000.0);
+  m->in.dmax_mm = (float)(c.max_ray_length * 1000.0);
+  m->in.vs = (float)c.voxel_scale;
+  m->in.max_steps = (float)(c.max_ray_length / c.voxel_scale);
+  m->in.max_ray = (float)c.max_ray_length;
+  m->in.internal_voxels = c.internal_voxels;
+  m->in.step = c.recast_step;
+}
+
+extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** out) {
+  if (!cfg || !out) { ts_set_error("null argument"); return TSLAM_E_INVALID; }
+  *out = nullptr;
+  if (cfg->voxel_scale <= 0 || cfg->N <= 0 || cfg->Nz <= 0 || cfg->recast_step <= 0 || cfg->N > 16384 || cfg->Nz > 16384) {
+    ts_set_error("invalid config (voxel_scale/N/Nz/recast_step)");
+    return TSLAM_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    ts_set_error("no CUDA device visible: libtslam has no CPU fallback");
+    return TSLAM_E_NOGPU;
+  }
+  tslam_tsdf* m = new tslam_tsdf();
+  memset(m, 0, sizeof(*m));
+  m->cfg = *cfg;
+  TS_CUDA(cudaGetDevice(&m->device));
+  cudaDeviceProp prop;
+  TS_CUDA(cudaGetDeviceProperties(&prop, m->device));
+  m->sm_count = prop.multiProcessorCount;
+  if (m->cfg.max_submaps <= 0) m->cfg.max_submaps = 1024;
+  if (m->cfg.max_submaps > 1024) m->cfg.max_submaps = 1024;
+  if (m->cfg.max_image_pixels <= 0) m->cfg.max_image_pixels = 640 * 480;
+  if (m->cfg.max_points <= 0) m->cfg.max_points = 1 << 20;
+  // block pool capacity: the dense block count when that is small, else 32768 blocks
+  const long long nb = (long long)((cfg->N + TS_B - 1) / TS_B + 1);
+  const long long nbz = (long long)((cfg->Nz + TS_B - 1) / TS_B + 1);
+  long long dense_blocks = nb * nb * nbz * (cfg->is_global_map ? 1 : 4);
+  if (m->cfg.max_blocks <= 0) m->cfg.max_blocks = (int)(dense_blocks < 32768 ? dense_blocks : 32768);
+  if (m->cfg.max_blocks > TS_MAX_BLOCKS) m->cfg.max_blocks = TS_MAX_BLOCKS;
+  ts_fill_intrin(m);
+  m->clamp_on_commit = true;
+
+  TsGrid& g = m->g;
+  g.max_blocks = m->cfg.max_blocks;
+  g.N = cfg->N; g.Nz = cfg->Nz; g.hN = cfg->N / 2; g.hNz = cfg->Nz / 2;
+  m->table_cap = next_pow2((size_t)g.max_blocks * 2 + 64);
+  g.table_mask = (uint32_t)(m->table_cap - 1);
+  const size_t nv = (size_t)g.max_blocks * TS_B3;
+  TS_CUDA(cudaMalloc(&g.table, m->table_cap * 8));
+  TS_CUDA(cudaMemset(g.table, 0xFF, m->table_cap * 8));
+  TS_CUDA(cudaMalloc(&g.block_key, (size_t)g.max_blocks * 8));
+  TS_CUDA(cudaMalloc(&g.acc, nv * sizeof(float2)));
+  TS_CUDA(cudaMalloc(&g.tw, nv * sizeof(float2)));
+  TS_CUDA(cudaMalloc(&g.obs, nv));
+  TS_CUDA(cudaMalloc(&g.occ, nv));
+  TS_CUDA(cudaMemset(g.acc, 0, nv * sizeof(float2)));
+  TS_CUDA(cudaMemset(g.tw, 0, nv * sizeof(float2)));
+  TS_CUDA(cudaMemset(g.obs, 0, nv));
+  TS_CUDA(cudaMemset(g.occ, 0, nv));
+  g.esdf = nullptr;
+  TS_CUDA(cudaMalloc(&g.dirty_flag, (size_t)g.max_blocks * 4));
+  TS_CUDA(cudaMalloc(&g.dirty_list, (size_t)g.max_blocks * 4));
+  TS_CUDA(cudaMemset(g.dirty_flag, 0, (size_t)g.max_blocks * 4));
+  TS_CUDA(cudaMalloc(&m->scratch_i, 64 * sizeof(int)));
+  TS_CUDA(cudaMemset(m->scratch_i, 0, 64 * sizeof(int)));
+  g.n_blocks = m->scratch_i + 0;
+  g.n_dirty = m->scratch_i + 1;
+  g.err = m->scratch_i + 2;
+  m->n_rays = m->scratch_i + 3;
+
+  // integrate workspace
+  const int step = m->cfg.recast_step;
+  size_t sampled = (size_t)m->cfg.max_image_pixels / ((size_t)step * step) + 1024;
+  m->bucket_cap = (uint32_t)next_pow2(sampled + sampled / 2);
+  // the point-cloud path treats the TSLAM_MAX_BATCH per-frame tables as ONE table
+  if ((size_t)m->cfg.max_points * 3 / 2 > (size_t)TSLAM_MAX_BATCH * m->bucket_cap) {
+    ts_set_error("max_points=%d too large for the bucket workspace", m->cfg.max_points);
+    return TSLAM_E_INVALID;
+  }
+  TS_CUDA(cudaMalloc(&m->buckets, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
+  TS_CUDA(cudaMemset(m->buckets, 0, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
+  m->ray_list_cap = (uint32_t)((size_t)TSLAM_MAX_BATCH * sampled);
+  if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
+  TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
+  TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));
+  TS_CUDA(cudaMalloc(&m->points_stage, (size_t)m->cfg.max_points * 12));
+  TS_CUDA(cudaMalloc(&m->counters, sizeof(TsCounters)));
+  TS_CUDA(cudaMemset(m->counters, 0, sizeof(TsCounters)));
+  TS_CUDA(cudaMalloc(&m->pose_R, (size_t)m->cfg.max_submaps * 9 * 4));
+  TS_CUDA(cudaMalloc(&m->pose_T, (size_t)m->cfg.max_submaps * 3 * 4));
+  TS_CUDA(cudaMemset(m->pose_R, 0, (size_t)m->cfg.max_submaps * 9 * 4));  // ti fields start at zero
+  TS_CUDA(cudaMemset(m->pose_T, 0, (size_t)m->cfg.max_submaps * 3 * 4));
+  std::vector<float> cm(1024 * 3);
+  fill_jet_host(cm.data());
+  TS_CUDA(cudaMalloc(&m->colormap, cm.size() * 4));
+  TS_CUDA(cudaMemcpy(m->colormap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice));
+  TS_CUDA(cudaDeviceSynchronize());
+  *out = m;
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
+  if (!m) return TSLAM_OK;
+  cudaDeviceSynchronize();
+  TsGrid& g = m->g;
+  cudaFree(g.table); cudaFree(g.block_key); cudaFree(g.acc); cudaFree(g.tw); cudaFree(g.obs); cudaFree(g.occ);
+  if (g.esdf) cudaFree(g.esdf);
+  cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
+  cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
+  cudaFree(m->counters); cudaFree(m->pose_R); cudaFree(m->pose_T); cudaFree(m->colormap);
+  if (m->ev) { for (int i = 0; i < 4 * TS_PROF_RING; i++) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
+  delete m;
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  TsGrid& g = m->g;
+  int nb = 0;
+  m->n_integrate_calls = 0;  // pending sums are discarded with the blocks
+  TS_CUDA(cudaMemcpyAsync(&nb, g.n_blocks, 4, cudaMemcpyDeviceToHost, st));
+  TS_CUDA(cudaStreamSynchronize(st));
+  if (nb > g.max_blocks) nb = g.max_blocks;
+  const size_t nv = (size_t)nb * TS_B3;
+  TS_CUDA(cudaMemsetAsync(g.table, 0xFF, m->table_cap * 8, st));
+  if (nv) {
+    TS_CUDA(cudaMemsetAsync(g.acc, 0, nv * sizeof(float2), st));
+    TS_CUDA(cudaMemsetAsync(g.tw, 0, nv * sizeof(float2), st));
+    TS_CUDA(cudaMemsetAsync(g.obs, 0, nv, st));
+    TS_CUDA(cudaMemsetAsync(g.occ, 0, nv, st));
+    if (g.esdf) TS_CUDA(cudaMemsetAsync(g.esdf, 0, nv * 4, st));
+    TS_CUDA(cudaMemsetAsync(g.dirty_flag, 0, (size_t)nb * 4, st));
+  }
+  TS_CUDA(cudaMemsetAsync(m->scratch_i, 0, 4 * sizeof(int), st));  // n_blocks, n_dirty, err, n_rays
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_set_intrinsics(tslam_tsdf_t* m, double fx, double fy, double cx, double cy) {
+  if (!m) return TSLAM_E_INVALID;
+  m->cfg.fx = fx; m->cfg.fy = fy; m->cfg.cx = cx; m->cfg.cy = cy;
+  ts_fill_intrin(m);
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_set_submap_pose(tslam_tsdf_t* m, int32_t s, const float* R9, const float* T3) {
+  if (!m || !R9 || !T3 || s < 0 || s >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", s); return TSLAM_E_INVALID; }
+  TS_CUDA(cudaMemcpy(m->pose_R + 9 * (size_t)s, R9, 36, cudaMemcpyHostToDevice));
+  TS_CUDA(cudaMemcpy(m->pose_T + 3 * (size_t)s, T3, 12, cudaMemcpyHostToDevice));
+  return TSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host: integrate
+// ---------------------------------------------------------------------------
+static int ts_launch_commit(tslam_tsdf* m, cudaStream_t st, int clamp, int fused) {
+  int grid = m->sm_count * 8;
+  k_commit<<<grid, 256, 0, st>>>(m->g, clamp, fused);
+  TS_LAUNCH_CHECK(m);
+  k_reset_counters<<<1, 1, 0, st>>>(m->g.n_dirty, nullptr);
+  TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
+
+int ts_flush_pending(tslam_tsdf* m, cudaStream_t st) {
+  if (m->n_integrate_calls > 0) {  // something may be pending
+    int rc = ts_launch_commit(m, st, m->clamp_on_commit ? 1 : 0, 0);
+    if (rc) return rc;
+    m->n_integrate_calls = 0;
+  }
+  return TSLAM_OK;
+}
+
+int ts_check_deferred(tslam_tsdf* m) {
+  int err = 0;
+  TS_CUDA(cudaMemcpy(&err, m->g.err, 4, cudaMemcpyDeviceToHost));
+  if (err) {
+    int zero = 0;
+    cudaMemcpy(m->g.err, &zero, 4, cudaMemcpyHostToDevice);
+    if (err & TS_ERR_POOL_FULL) { ts_set_error("voxel-block pool exhausted (max_blocks=%d): samples were dropped", m->g.max_blocks); return TSLAM_E_POOL_FULL; }
+    ts_set_error("device error flags 0x%x (hash table / ray list capacity)", err);
+    return TSLAM_E_CAPACITY;
+  }
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_commit(tslam_tsdf_t* m, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  return ts_flush_pending(m, (cudaStream_t)stream);
+}
+
+static void ts_fill_frame(TsFrame& fr, const float* R9, const float* T3, int submap) {
+  memcpy(fr.R, R9, 36);
+  memcpy(fr.T, T3, 12);
+  fr.submap = submap;
+}
+
+extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
+                                          const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream) {
+  if (!m || !depth || !R9s || !T3s || n_frames < 0 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int step = m->cfg.recast_step;
+  const int hh = (int)((double)h / step), ww = (int)((double)w / step);  // range(0, h/step) (dense_tsdf.py:192,194)
+  if (hh <= 0 || ww <= 0) return TSLAM_OK;
+  uint32_t bshift = 0;
+  while ((1u << bshift) < m->bucket_cap) bshift++;
+  for (int base = 0; base < n_frames; base += TSLAM_MAX_BATCH) {
+    const int nf = (n_frames - base < TSLAM_MAX_BATCH) ? (n_frames - base) : TSLAM_MAX_BATCH;
+    TsBatch batch;
+    for (int q = 0; q < nf; q++) {
+      const int sid = submap_ids ? submap_ids[base + q] : 0;
+      if (sid < 0 || sid >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", sid); return TSLAM_E_INVALID; }
+      ts_fill_frame(batch.f[q], R9s + 9 * (size_t)(base + q), T3s + 3 * (size_t)(base + q), sid);
+    }
+    const uint16_t* src = depth + (size_t)base * h * w;
+    if (mem == TSLAM_MEM_HOST) {
+      TS_CUDA(cudaMemcpyAsync(m->depth_stage, src, (size_t)nf * h * w * 2, cudaMemcpyHostToDevice, st));
+      src = m->depth_stage;
+    }
+    cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
+    if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
+    dim3 grid1((hh * ww + 255) / 256, nf);
+    k_bucket_depth<<<grid1, 256, 0, st>>>(src, h, w, hh, ww, batch, m->in, m->buckets, m->bucket_cap, m->ray_list, m->n_rays,
+                                          m->ray_list_cap, m->counters, m->g.err);
+    TS_LAUNCH_CHECK(m);
+    if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
+    k_raymarch<<<m->sm_count * 16, 128, 0, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays, m->ray_list_cap,
+                                                 m->counters);
+    TS_LAUNCH_CHECK(m);
+    if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
+    k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
+    TS_LAUNCH_CHECK(m);
+    m->n_integrate_calls++;
+    if (flags & TSLAM_F_COMMIT) {
+      int rc = ts_flush_pending(m, st);
+      if (rc) return rc;
+    }
+    if (pe) { TS_CUDA(cudaEventRecord(pe[3], st)); m->prof_launches++; }
+  }
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
+                                           int32_t submap, int flags, void* stream) {
+  if (!m || (!xyz && n > 0) || !R9 || !T3 || n < 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if (n > m->cfg.max_points) { ts_set_error("n=%d exceeds max_points=%d", n, m->cfg.max_points); return TSLAM_E_INVALID; }
+  if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
+  if (n == 0) return TSLAM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  TsBatch batch;
+  ts_fill_frame(batch.f[0], R9, T3, submap);
+  const float* src = xyz;
+  if (mem == TSLAM_MEM_HOST) {
+    TS_CUDA(cudaMemcpyAsync(m->points_stage, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    src = m->points_stage;
+  }
+  const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
+  const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
+  cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
+    if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
+  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, m->buckets, cap_total, m->ray_list, m->n_rays,
+                                                    m->ray_list_cap, m->counters, m->g.err);
+  TS_LAUNCH_CHECK(m);
+  if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
+  k_raymarch<<<m->sm_count * 16, 128, 0, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays, m->ray_list_cap,
+                                               m->counters);
+  TS_LAUNCH_CHECK(m);
+  if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
+  k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
+  TS_LAUNCH_CHECK(m);
+  m->n_integrate_calls++;
+  if (flags & TSLAM_F_COMMIT) {
+    int rc = ts_flush_pending(m, st);
+    if (rc) return rc;
+  }
+  if (pe) { TS_CUDA(cudaEventRecord(pe[3], st)); m->prof_launches++; }
+  return TSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// count / gather / scatter  (dense_tsdf.py:412-454)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count_active(TsGrid g, int submap, unsigned long long* out) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  unsigned int c = 0;
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    int s, bx, by, bz;
+    ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (s != submap) continue;
+    const uint8_t* obs = g.obs + (size_t)b * TS_B3;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) c += obs[v] > 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// warp-aggregated append: returns the output row of this lane (or -1)
+__device__ __forceinline__ long long warp_append(bool want, unsigned long long* counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return want ? (long long)(base + __popc(m & ((1u << lane) - 1))) : -1;
+}
+__device__ __forceinline__ int warp_append_i32(bool want, int* counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return want ? base + __popc(m & ((1u << lane) - 1)) : -1;
+}
+
+__global__ void __launch_bounds__(256) k_gather(TsGrid g, int submap, long long cap, int32_t* idx, float* tsdf, float* wts,
+                                                 int8_t* occ, unsigned long long* counter) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    int s, bx, by, bz;
+    ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (s != submap) continue;
+    const size_t base = (size_t)b * TS_B3;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      const bool want = g.obs[base + v] > 0;
+      const long long row = warp_append(want, counter);
+      if (want && row < cap) {
+        idx[3 * row] = bx * TS_B + (v >> 8);
+        idx[3 * row + 1] = by * TS_B + ((v >> 4) & 15);
+        idx[3 * row + 2] = bz * TS_B + (v & 15);
+        const float2 t = g.tw[base + v];
+        tsdf[row] = t.x;
+        wts[row] = t.y;
+        occ[row] = g.occ[base + v];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(TsGrid g, int submap, long long n, const int32_t* idx, const float* tsdf,
+                                                  const float* wts, const int8_t* occ) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const int i = idx[3 * r], j = idx[3 * r + 1], k = idx[3 * r + 2];
+    if (!ts_in_bounds(g, i, j, k)) continue;
+    const int blk = ts_get_or_alloc(g, ts_pack_key(submap, i >> TS_BSHIFT, j >> TS_BSHIFT, k >> TS_BSHIFT));
+    if (blk < 0) continue;
+    const size_t o = (size_t)blk * TS_B3 + ts_voxel_off(i, j, k);
+    g.tw[o] = make_float2(tsdf[r], wts[r]);  // :447-448
+    g.occ[o] = occ[r];                        // :449
+    g.obs[o] = 1;                             // :454
+  }
+}
+
+extern "C" int tslam_tsdf_count_active(tslam_tsdf_t* m, int32_t submap, int64_t* n_out) {
+  if (!m || !n_out) return TSLAM_E_INVALID;
+  cudaStream_t st = 0;
+  int rc = ts_flush_pending(m, st);
+  if (rc) return rc;
+  unsigned long long* ctr = (unsigned long long*)(m->scratch_i + 8);
+  TS_CUDA(cudaMemsetAsync(ctr, 0, 8, st));
+  k_count_active<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, ctr);
+  TS_LAUNCH_CHECK(m);
+  unsigned long long v = 0;
+  TS_CUDA(cudaMemcpy(&v, ctr, 8, cudaMemcpyDeviceToHost));
+  *n_out = (int64_t)v;
+  return ts_check_deferred(m);
+}
+
+extern "C" int tslam_tsdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* tsdf, float* w, int8_t* occ,
+                                 int64_t* n_out, void* stream) {
+  if (!m || !n_out) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(m, st);
+  if (rc) return rc;
+  unsigned long long* ctr = (unsigned long long*)(m->scratch_i + 8);
+  TS_CUDA(cudaMemsetAsync(ctr, 0, 8, st));
+  k_gather<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, cap, idx, tsdf, w, occ, ctr);
+  TS_LAUNCH_CHECK(m);
+  unsigned long long v = 0;
+  TS_CUDA(cudaMemcpyAsync(&v, ctr, 8, cudaMemcpyDeviceToHost, st));
+  TS_CUDA(cudaStreamSynchronize(st));
+  *n_out = (int64_t)v;
+  rc = ts_check_deferred(m);
+  if (rc) return rc;
+  if ((int64_t)v > cap) { ts_set_error("gather: %lld observed voxels > capacity %lld", (long long)v, (long long)cap); return TSLAM_E_CAPACITY; }
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_scatter(tslam_tsdf_t* m, int32_t submap, int64_t n, const int32_t* idx, const float* tsdf, const float* w,
+                                  const int8_t* occ, void* stream) {
+  if (!m || n < 0 || submap < 0 || submap >= m->cfg.max_submaps) return TSLAM_E_INVALID;
+  if (n == 0) return TSLAM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(m, st);
+  if (rc) return rc;
+  int grid = (int)((n + 255) / 256);
+  if (grid > m->sm_count * 32) grid = m->sm_count * 32;
+  k_scatter<<<grid, 256, 0, st>>>(m->g, submap, n, idx, tsdf, w, occ);
+  TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// exporters  (dense_tsdf.py:339-385)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void voxel_xyz(const TsGrid& g, bool global_map, const float* pR, const float* pT, int s, int i, int j,
+                                          int k, float vs, float& x, float& y, float& z) {
+  const float lx = (float)i * vs, ly = (float)j * vs, lz = (float)k * vs;  // ijk_to_xyz mapping_common.py:221-223
+  if (global_map) { x = lx; y = ly; z = lz; return; }                      // i_j_k_to_xyz
+  const float* R = pR + 9 * s;                                             // submap_i_j_k_to_xyz :229-232
+  const float* T = pT + 3 * s;
+  x = ((R[0] * lx + R[1] * ly) + R[2] * lz) + T[0];
+  y = ((R[3] * lx + R[4] * ly) + R[5] * lz) + T[1];
+  z = ((R[6] * lx + R[7] * ly) + R[8] * lz) + T[2];
+}
+
+__global__ void __launch_bounds__(256) k_extract_surface(TsGrid g, int submap, int global_map, const float* pR, const float* pT,
+                                                          float vs, float thres, float fl, float ce, const float* cmap,
+                                                          long long cap, float* xyz, float* rgb, int* counter) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    int s, bx, by, bz;
+    ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (s != submap) continue;  // :348
+    const size_t base = (size_t)b * TS_B3;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      bool want = false;
+      float x = 0, y = 0, z = 0;
+      if (g.obs[base + v] == 1) {                      // :349
+        const float t = g.tw[base + v].x;
+        if (fabsf(t) < thres) {                        // :350
+          voxel_xyz(g, global_map, pR, pT, s, bx * TS_B + (v >> 8), by * TS_B + ((v >> 4) & 15), bz * TS_B + (v & 15), vs, x, y, z);
+          want = !(z > ce || z < fl);                  // :356
+        }
+      }
+      const int row = warp_append_i32(want, counter);  // :358
+      if (want && row < cap) {                         // :359 (saturating)
+        xyz[3 * (size_t)row] = x; xyz[3 * (size_t)row + 1] = y; xyz[3 * (size_t)row + 2] = z;
+        if (rgb) {
+          const int ci = (int)fmaxf(fminf(((z - fl) / (ce - fl)) * 1023.0f, 1023.0f), 0.0f);  // mapping_common.py:216-219
+          rgb[3 * (size_t)row] = cmap[3 * ci]; rgb[3 * (size_t)row + 1] = cmap[3 * ci + 1]; rgb[3 * (size_t)row + 2] = cmap[3 * ci + 2];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_extract_slice(TsGrid g, int submap, int global_map, const float* pR, const float* pT,
+                                                        float vs, int index, float dz, const float* cmap, long long cap,
+                                                        float* xyz, float* val, float* rgb, int* counter) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    int s, bx, by, bz;
+    ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (s != submap) continue;  // :375
+    const size_t base = (size_t)b * TS_B3;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      const int k = bz * TS_B + (v & 15);
+      const bool want = g.obs[base + v] > 0 && ((float)index - dz < (float)k) && ((float)k < (float)index + dz);  // :376-377
+      const int row = warp_append_i32(want, counter);
+      if (want && row < cap) {
+        float x, y, z;
+        voxel_xyz(g, global_map, pR, pT, s, bx * TS_B + (v >> 8), by * TS_B + ((v >> 4) & 15), k, vs, x, y, z);
+        const float t = g.tw[base + v].x;
+        xyz[3 * (size_t)row] = x; xyz[3 * (size_t)row + 1] = y; xyz[3 * (size_t)row + 2] = z;
+        if (val) val[row] = t;  // :380
+        if (rgb) {
+          const int ci = (int)fmaxf(fminf(((t - (-0.5f)) / (0.5f - (-0.5f))) * 1023.0f, 1023.0f), 0.0f);  // :385
+          rgb[3 * (size_t)row] = cmap[3 * ci]; rgb[3 * (size_t)row + 1] = cmap[3 * ci + 1]; rgb[3 * (size_t)row + 2] = cmap[3 * ci + 2];
+        }
+      }
+    }
+  }
+}
+
+extern "C" int tslam_tsdf_extract_surface(tslam_tsdf_t* m, int32_t submap, int64_t cap, float* xyz, float* rgb, int32_t* count_dev,
+                                          void* stream) {
+  if (!m || !xyz || !count_dev) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(m, st);
+  if (rc) return rc;
+  const float thres = (float)(m->cfg.voxel_scale * 1.8);  // dense_tsdf.py:39
+  k_extract_surface<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, m->cfg.is_global_map, m->pose_R, m->pose_T, m->in.vs, thres,
+                                                     (float)m->cfg.disp_floor, (float)m->cfg.disp_ceiling, m->colormap, cap, xyz,
+                                                     rgb, count_dev);
+  TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
+
+static float h16_round(float x) {  // slice_z is an f16 field (dense_tsdf.py:72)
+  __half hv = __float2half_rn(x);
+  return __half2float(hv);
+}
+
+extern "C" int tslam_tsdf_extract_slice(tslam_tsdf_t* m, int32_t submap, float z, float dz, int64_t cap, float* xyz, float* val,
+                                        float* rgb, int32_t* count_dev, void* stream) {
+  if (!m || !xyz || !count_dev) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(m, st);
+  if (rc) return rc;
+  const int index = (int)(h16_round(z) / m->in.vs);  // :369-370
+  k_extract_slice<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, m->cfg.is_global_map, m->pose_R, m->pose_T, m->in.vs, index, dz,
+                                                   m->colormap, cap, xyz, val, rgb, count_dev);
+  TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// submap -> global fusion  (dense_tsdf.py:272-318)
+// One CTA per SOURCE block; each observed source voxel splats into the 7 upper
+// trilinear corners (:297-300) with one 8-byte reduction per corner; commit
+// (no Wmax clamp, :274-278) turns the sums into (TSDF, W).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void sat_add_i8(int8_t* p, int add) {
+  if (add == 0) return;
+  unsigned int* wp = (unsigned int*)((uintptr_t)p & ~(uintptr_t)3);
+  const int sh = (int)((uintptr_t)p & 3) * 8;
+  unsigned int old = *wp, assumed;
+  do {
+    assumed = old;
+    int cur = (int)(int8_t)((assumed >> sh) & 0xFF);
+    int nv = cur + add;
+    nv = nv > 127 ? 127 : (nv < -128 ? -128 : nv);  // reference wraps (i8); we saturate
+    unsigned int repl = (assumed & ~(0xFFu << sh)) | (((unsigned int)(nv & 0xFF)) << sh);
+    old = atomicCAS(wp, assumed, repl);
+  } while (old != assumed);
+}
+
+__global__ void __launch_bounds__(256) k_fuse(TsGrid dst, TsGrid src, const float* pR, const float* pT, float vs) {
+  const int nb = min(*src.n_blocks, src.max_blocks);
+  for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+    int s, bx, by, bz;
+    ts_unpack_key(src.block_key[b], s, bx, by, bz);
+    const float* R = pR + 9 * s;
+    const float* T = pT + 3 * s;
+    const size_t base = (size_t)b * TS_B3;
+    unsigned long long cur_key = TS_EMPTY;
+    int cur_blk = -1;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      if (!(src.obs[base + v] > 0)) continue;  // :292
+      const float2 t = src.tw[base + v];
+      const int occ = src.occ[base + v];
+      const float lx = (float)(bx * TS_B + (v >> 8)) * vs, ly = (float)(by * TS_B + ((v >> 4) & 15)) * vs,
+                  lz = (float)(bz * TS_B + (v & 15)) * vs;
+      const float gx = (((R[0] * lx + R[1] * ly) + R[2] * lz) + T[0]) / vs;  // :293-294
+      const float gy = (((R[3] * lx + R[4] * ly) + R[5] * lz) + T[1]) / vs;
+      const float gz = (((R[6] * lx + R[7] * ly) + R[8] * lz) + T[2]) / vs;
+      const int lo0 = (int)floorf(gx), lo1 = (int)floorf(gy), lo2 = (int)floorf(gz);  // :296
+#pragma unroll
+      for (int c = 1; c < 8; c++) {  // c=0 (di=dj=dk=0) skipped: reference quirk :300
+        const int ci = lo0 + ((c >> 2) & 1), cj = lo1 + ((c >> 1) & 1), ck = lo2 + (c & 1);
+        const float wt = (1.0f - fabsf((float)ci - gx)) * (1.0f - fabsf((float)cj - gy)) * (1.0f - fabsf((float)ck - gz));  // :303
+        if (!ts_in_bounds(dst, ci, cj, ck)) continue;
+        const unsigned long long key = ts_pack_key(0, ci >> TS_BSHIFT, cj >> TS_BSHIFT, ck >> TS_BSHIFT);
+        if (key != cur_key) {
+          cur_key = key;
+          cur_blk = ts_get_or_alloc(dst, key);
+          if (cur_blk >= 0) ts_mark_dirty(dst, cur_blk);
+        }
+        if (cur_blk < 0) continue;
+        const size_t o = (size_t)cur_blk * TS_B3 + ts_voxel_off(ci, cj, ck);
+        const float w = t.y * wt;                    // :307
+        red_add_f32x2(&dst.acc[o], w * t.x, w);      // :274-275
+        if (dst.obs[o] == 0) dst.obs[o] = 2;         // :279 observed, value pending (2 -> 1 at commit)
+        sat_add_i8(&dst.occ[o], occ);                // :280
+      }
+    }
+  }
+}
+
+extern "C" int tslam_tsdf_fuse(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* stream) {
+  if (!dst || !src || dst == src) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(src, st);
+  if (rc) return rc;
+  dst->n_integrate_calls = 0;  // pending updates of dst are discarded by reset() (:312-313)
+  rc = tslam_tsdf_reset(dst, stream);
+  if (rc) return rc;
+  k_fuse<<<dst->sm_count * 8, 256, 0, st>>>(dst->g, src->g, dst->pose_R, dst->pose_T, dst->in.vs);
+  TS_LAUNCH_CHECK(dst);
+  return ts_launch_commit(dst, st, 0, 1);
+}
+
+// ---------------------------------------------------------------------------
+// stats / sync / profiling
+// ---------------------------------------------------------------------------
+extern "C" int tslam_tsdf_get_stats(tslam_tsdf_t* m, int64_t* out8, int clear) {
+  if (!m || !out8) return TSLAM_E_INVALID;
+  TS_CUDA(cudaDeviceSynchronize());
+  TsCounters c;
+  TS_CUDA(cudaMemcpy(&c, m->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  int sc[4];
+  TS_CUDA(cudaMemcpy(sc, m->scratch_i, sizeof(sc), cudaMemcpyDeviceToHost));
+  out8[0] = (int64_t)c.n_px; out8[1] = (int64_t)c.n_valid; out8[2] = (int64_t)c.n_rays; out8[3] = (int64_t)c.n_updates;
+  out8[4] = (int64_t)c.n_oob; out8[5] = sc[0]; out8[6] = sc[2]; out8[7] = m->launches;
+  if (clear) TS_CUDA(cudaMemset(m->counters, 0, sizeof(TsCounters)));
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_sync(tslam_tsdf_t* m, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  TS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ts_check_deferred(m);
+}
+
+extern "C" int64_t tslam_tsdf_launch_count(tslam_tsdf_t* m) { return m ? m->launches : 0; }
+
+extern "C" int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on) {
+  if (!m) return TSLAM_E_INVALID;
+  if (on && !m->ev) {
+    m->ev = new cudaEvent_t[4 * TS_PROF_RING];
+    for (int i = 0; i < 4 * TS_PROF_RING; i++) TS_CUDA(cudaEventCreate(&m->ev[i]));
+  }
+  m->profiling = on;
+  m->prof_launches = 0;
+  return TSLAM_OK;
+}
+// ms3[3*i + {0,1,2}] = bucket / ray-march / commit(+reset) kernel time of the i-th most recent
+// recorded integrate launch, i < n (n <= TS_PROF_RING).  Returns the number of rows written in *n_out.
+extern "C" int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out) {
+  if (!m || !ms3 || !n_out || !m->ev) return TSLAM_E_INVALID;
+  TS_CUDA(cudaDeviceSynchronize());
+  long long have = m->prof_launches < TS_PROF_RING ? m->prof_launches : TS_PROF_RING;
+  if (n > have) n = (int32_t)have;
+  for (int i = 0; i < n; i++) {
+    cudaEvent_t* pe = m->ev + 4 * ((m->prof_launches - 1 - i) % TS_PROF_RING);
+    for (int q = 0; q < 3; q++) TS_CUDA(cudaEventElapsedTime(&ms3[3 * i + q], pe[q], pe[q + 1]));
+  }
+  *n_out = n;
+  return TSLAM_OK;
+}

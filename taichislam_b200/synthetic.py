@@ -38,7 +38,9 @@ def scene_room(seed=3, h=H, w=W):
     """A box room with a few depth steps and invalid (0) holes - exercises the range filter."""
     rng = np.random.default_rng(seed)
     u, v = _uv(h, w)
-    z = np.minimum.reduce([np.full((h, w), 5.0), 2.5 / np.maximum(np.abs(u), 1e-3), 1.6 / np.maximum(np.abs(v), 1e-3)])
+    u = np.broadcast_to(u, (h, w))
+    v = np.broadcast_to(v, (h, w))
+    z = np.minimum(np.minimum(np.full((h, w), 5.0), 2.5 / np.maximum(np.abs(u), 1e-3)), 1.6 / np.maximum(np.abs(v), 1e-3))
     d = np.round(z * 1000.0)
     d[rng.random((h, w)) < 0.02] = 0          # dropouts
     d[40:80, 50:120] = 150                   # closer than min_ray

@@ -204,9 +204,16 @@ def main():
         pool.append(torch.from_numpy(np.ascontiguousarray(d).view(np.int16)).cuda())
     frame_t = rank * 100000  # every rank integrates its own stretch of the stream into its own map (submap sharding)
 
+    n_steps_total = args.warmup + args.steps
+    Rs_all, Ts_all = syn.stream_poses(n_steps_total * BATCH, start=frame_t)   # host pose stream, prepared up front
+    Rs_all = np.ascontiguousarray(Rs_all.astype(np.float32).reshape(n_steps_total, BATCH, 9))
+    Ts_all = np.ascontiguousarray(Ts_all.astype(np.float32).reshape(n_steps_total, BATCH, 3))
+    step_no = [0]
+
     def step_dev(i, t):
-        _, Rs, Ts = make_inputs(BATCH, t)
-        g.integrate_depth(pool[i % POOL_BATCHES], Rs, Ts, commit=True)
+        k = step_no[0]
+        step_no[0] += 1
+        g.integrate_depth(pool[i % POOL_BATCHES], Rs_all[k], Ts_all[k], commit=True)
 
     for i in range(args.warmup):
         step_dev(i, frame_t)

@@ -177,6 +177,8 @@ int tslam_octo_create(const tslam_octo_config_t* cfg, tslam_octo_t** out);
 int tslam_octo_destroy(tslam_octo_t* m);
 int tslam_octo_reset(tslam_octo_t* m, void* stream); /* root.deactivate_all() taichi_octomap.py:210-211 */
 int tslam_octo_set_submap_pose(tslam_octo_t* m, int32_t s, const float* R9, const float* T3);
+/* BaseMap.set_dep_camera_intrinsic (mapping_common.py:25-26). */
+int tslam_octo_set_intrinsics(tslam_octo_t* m, double fx, double fy, double cx, double cy);
 /* recast_pcl_to_map_kernel (taichi_octomap.py:134-145): occupy[round((R p + T)/vs)] += 1. */
 int tslam_octo_integrate_points(tslam_octo_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
                                 int32_t submap, void* stream);

@@ -673,12 +673,18 @@ int64_t orc_mc(void* h, int step, float thres, int64_t cap_tri, float* verts, fl
             const float* p = vl[es[q]];
             float* vo = verts + (ntri * 3 + q) * 3;
             vo[0] = p[0] * vs; vo[1] = p[1] * vs; vo[2] = p[2] * vs;  // ijk_to_xyz :40-42
+            float* no = normals + (ntri * 3 + q) * 3;
+            if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) {
+              // NaN TSDF corner (the shipped fixtures contain some) -> NaN vertex; round(NaN) is undefined in the
+              // reference (:86).  Canonical: the normal of a non-finite vertex is NaN.
+              no[0] = no[1] = no[2] = NAN;
+              continue;
+            }
             int pi = iround(p[0]), pj = iround(p[1]), pk = iround(p[2]);  // generate_normal :84-93
             float nx = m->readT(s, pi + 1, pj, pk) - m->readT(s, pi - 1, pj, pk);
             float ny = m->readT(s, pi, pj + 1, pk) - m->readT(s, pi, pj - 1, pk);
             float nz = m->readT(s, pi, pj, pk + 1) - m->readT(s, pi, pj, pk - 1);
             float nn = sqrtf((nx * nx + ny * ny) + nz * nz);
-            float* no = normals + (ntri * 3 + q) * 3;
             no[0] = nx / nn; no[1] = ny / nn; no[2] = nz / nn;  // normalized(): NaN when the gradient is 0
           }
         }

@@ -79,6 +79,7 @@ SIGNATURES = {
     "tslam_octo_destroy": (C.c_int, [_vp]),
     "tslam_octo_reset": (C.c_int, [_vp, _vp]),
     "tslam_octo_set_submap_pose": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "tslam_octo_set_intrinsics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "tslam_octo_integrate_points": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _i32, _vp]),
     "tslam_octo_integrate_depth": (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _vp, _vp, _i32, _vp]),
     "tslam_octo_gather": (C.c_int, [_vp, _i32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),

@@ -246,12 +246,16 @@ __global__ void __launch_bounds__(256) k_mc_emit(TsGrid g, float thres, float vs
             float* vo = verts + ((size_t)tri * 3 + q) * 3;
             vo[0] = px * vs; vo[1] = py * vs; vo[2] = pz * vs;  // ijk_to_xyz :40-42 (map-local metres)
             // generate_normal :84-93 - central differences at round(vertex), from the staged tile
+            float* no = normals + ((size_t)tri * 3 + q) * 3;
+            if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {  // NaN TSDF corner: round(NaN) is undefined (:86)
+              no[0] = no[1] = no[2] = __int_as_float(0x7fc00000);
+              continue;
+            }
             const int qx = (int)roundf(px) - bx * TS_B, qy = (int)roundf(py) - by * TS_B, qz = (int)roundf(pz) - bz * TS_B;
             const float nx = tile.t[mc_tidx(qx + 1, qy, qz)] - tile.t[mc_tidx(qx - 1, qy, qz)];
             const float ny = tile.t[mc_tidx(qx, qy + 1, qz)] - tile.t[mc_tidx(qx, qy - 1, qz)];
             const float nz = tile.t[mc_tidx(qx, qy, qz + 1)] - tile.t[mc_tidx(qx, qy, qz - 1)];
             const float nn = sqrtf((nx * nx + ny * ny) + nz * nz);
-            float* no = normals + ((size_t)tri * 3 + q) * 3;
             no[0] = nx / nn; no[1] = ny / nn; no[2] = nz / nn;  // normalized(): NaN when the gradient vanishes
           }
         }
@@ -322,6 +326,11 @@ __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float th
           const float px = vl[e][0], py = vl[e][1], pz = vl[e][2];
           float* vo = verts + ((size_t)tri * 3 + q) * 3;
           vo[0] = px * vs; vo[1] = py * vs; vo[2] = pz * vs;
+          float* no = normals + ((size_t)tri * 3 + q) * 3;
+          if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
+            no[0] = no[1] = no[2] = __int_as_float(0x7fc00000);
+            continue;
+          }
           const int qx = (int)roundf(px), qy = (int)roundf(py), qz = (int)roundf(pz);
           float a0, a1;
           int o;
@@ -332,7 +341,6 @@ __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float th
           mc_read(g, s, qx, qy, qz + 1, a0, o); mc_read(g, s, qx, qy, qz - 1, a1, o);
           const float nz = a0 - a1;
           const float nn = sqrtf((nx * nx + ny * ny) + nz * nz);
-          float* no = normals + ((size_t)tri * 3 + q) * 3;
           no[0] = nx / nn; no[1] = ny / nn; no[2] = nz / nn;
         }
       }

@@ -241,6 +241,13 @@ extern "C" int tslam_octo_set_submap_pose(tslam_octo_t* m, int32_t s, const floa
   return TSLAM_OK;
 }
 
+extern "C" int tslam_octo_set_intrinsics(tslam_octo_t* m, double fx, double fy, double cx, double cy) {
+  if (!m) return TSLAM_E_INVALID;
+  m->cfg.fx = fx; m->cfg.fy = fy; m->cfg.cx = cx; m->cfg.cy = cy;
+  m->in.fx = (float)fx; m->in.fy = (float)fy; m->in.cx = (float)cx; m->in.cy = (float)cy;
+  return TSLAM_OK;
+}
+
 static int oc_deferred(tslam_octo* m) {
   int err = 0;
   TS_CUDA(cudaMemcpy(&err, m->g.err, 4, cudaMemcpyDeviceToHost));

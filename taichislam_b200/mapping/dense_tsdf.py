@@ -1,0 +1,288 @@
+"""DenseTSDF - the reference's class surface (taichi_slam/mapping/dense_tsdf.py) on libtslam.so.
+
+Same constructor kwargs, attributes and methods as the reference class;
+every method that launched a Taichi kernel now enqueues hand-written sm_100a kernels through
+the C ABI (include/tslam.h).  Like Taichi, calls are asynchronous: `recast_depth_to_map`
+queues the frame (pinned staging + pose) and frames are integrated in batches of up to 64 per
+launch; any reader (`count_active`, `to_numpy`, `cvt_*`, field reads, the mesher) flushes the
+queue first, so results are indistinguishable from per-frame execution.
+"""
+import math
+import time
+
+import numpy as np
+
+from .. import _capi as capi
+from ..tsdf_handle import TsdfHandle
+from .field import Field
+from .mapping_common import BaseMap
+
+Wmax = 1000  # dense_tsdf.py:8
+
+
+class DenseTSDF(BaseMap):
+    def __init__(self, map_scale=[10, 10], voxel_scale=0.05, texture_enabled=False,
+                 max_disp_particles=1024 * 1024, num_voxel_per_blk_axis=16, max_ray_length=10, min_ray_length=0.3,
+                 internal_voxels=10, max_submap_num=1024, is_global_map=False,
+                 disp_ceiling=1.8, disp_floor=-0.3, recast_step=2, color_same_proj=True,
+                 max_blocks=0, max_image_pixels=640 * 480):
+        super(DenseTSDF, self).__init__(voxel_scale)
+        import torch
+        self._torch = torch
+        # derived sizes exactly as dense_tsdf.py:18-31
+        self.num_voxel_per_blk_axis = num_voxel_per_blk_axis
+        self.voxel_scale = voxel_scale
+        self.N = math.ceil(map_scale[0] / voxel_scale / num_voxel_per_blk_axis) * num_voxel_per_blk_axis
+        self.Nz = math.ceil(map_scale[1] / voxel_scale / num_voxel_per_blk_axis) * num_voxel_per_blk_axis
+        self.block_num_xy = math.ceil(map_scale[0] / voxel_scale / num_voxel_per_blk_axis)
+        self.block_num_z = math.ceil(map_scale[1] / voxel_scale / num_voxel_per_blk_axis)
+        self.map_size_xy = voxel_scale * self.N
+        self.map_size_z = voxel_scale * self.Nz
+        self.max_disp_particles = max_disp_particles
+        self.enable_texture = texture_enabled
+        self.max_ray_length = max_ray_length
+        self.min_ray_length = min_ray_length
+        self.tsdf_surface_thres = self.voxel_scale * 1.8  # :39
+        self.internal_voxels = internal_voxels
+        self.max_submap_num = max_submap_num
+        self.is_global_map = is_global_map
+        self.disp_ceiling = disp_ceiling
+        self.disp_floor = disp_floor
+        self.recast_step = recast_step
+        self.color_same_proj = color_same_proj
+        self.clear_last_TSDF_exporting = False  # assigned by SubmapMapping (submap_mapping.py:134)
+        self.color = None  # texture path not built yet (second priority); geometry only
+        if texture_enabled:
+            print("[DenseTSDF/b200] texture_enabled=True: colour fusion is not implemented yet, geometry only")
+
+        self._h = TsdfHandle(self.N, self.Nz, voxel_scale=voxel_scale, max_ray_length=max_ray_length,
+                             min_ray_length=min_ray_length, internal_voxels=internal_voxels, recast_step=recast_step,
+                             K=None, is_global_map=is_global_map, disp_floor=disp_floor, disp_ceiling=disp_ceiling,
+                             max_submaps=min(max_submap_num, 1024), max_blocks=max_blocks,
+                             max_image_pixels=max_image_pixels)
+        self.initialize_submap_fields(self.max_submap_num)
+        self._init_export_fields()
+        # frame queue (pinned, double buffered)
+        self._qcap = capi.MAX_BATCH
+        self._stage = None
+        self._stage_shape = None
+        self._q_n = 0
+        self._q_buf = 0
+        self._q_R = np.zeros((self._qcap, 9), np.float32)
+        self._q_T = np.zeros((self._qcap, 3), np.float32)
+        self._q_s = np.zeros(self._qcap, np.int32)
+        self._stage_ev = [None, None]
+        print(f"TSDF map initialized blocks {self.block_num_xy}x{self.block_num_xy}x{self.block_num_z}")
+
+    # ------------------------------------------------------------------ fields (dense_tsdf.py:52-60, :129-134)
+    def _init_export_fields(self):
+        torch = self._torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n = self.max_disp_particles
+        fl = self._flush
+        self.num_export_particles = Field(torch.zeros(1, dtype=torch.int32, device=dev), fl)
+        self.num_TSDF_particles = Field(torch.zeros(1, dtype=torch.int32, device=dev), fl)
+        self.num_export_ESDF_particles = Field(torch.zeros(1, dtype=torch.int32, device=dev), fl)
+        self.export_x = Field(torch.full((n, 3), -100000.0, dtype=torch.float32, device=dev), fl)
+        self.export_color = Field(torch.full((n, 3), 0.5, dtype=torch.float32, device=dev), fl)
+        self.export_TSDF = Field(torch.zeros(n, dtype=torch.float32, device=dev), fl)
+        self.export_TSDF_xyz = Field(torch.full((n, 3), -100000.0, dtype=torch.float32, device=dev), fl)
+
+    def _on_intrinsics(self):
+        self._flush()
+        self._h.set_intrinsics(self.K_cam_dep)
+
+    def _upload_submap_pose(self, submap_id, R, T):
+        self._h.set_submap_pose(submap_id, R, T)
+
+    # ------------------------------------------------------------------ integrate (dense_tsdf.py:157-165)
+    def _ensure_stage(self, h, w):
+        torch = self._torch
+        if self._stage_shape != (h, w):
+            self._flush()
+            self._stage = [torch.empty((self._qcap, h, w), dtype=torch.int16).pin_memory() for _ in range(2)]
+            self._stage_np = [s.numpy().view(np.uint16) for s in self._stage]
+            self._stage_shape = (h, w)
+
+    def recast_depth_to_map(self, R, T, depthmap, texture):
+        """Queue one depth frame (uint16 mm [h,w]); integrated with the next batch (:162-165)."""
+        if self.K_cam_dep is None:
+            raise RuntimeError("set_dep_camera_intrinsic() must be called before recast_depth_to_map")
+        self.set_pose(R, T)
+        depthmap = np.asarray(depthmap)
+        h, w = depthmap.shape
+        self._ensure_stage(h, w)
+        if self._q_n == 0 and self._stage_ev[self._q_buf] is not None:
+            self._stage_ev[self._q_buf].synchronize()  # the previous H2D copy out of this buffer has finished
+        q = self._q_n
+        self._stage_np[self._q_buf][q] = depthmap
+        self._q_R[q] = self.input_R_np.reshape(9)
+        self._q_T[q] = self.input_T_np
+        self._q_s[q] = 0 if self.is_global_map else self.active_submap_id[None]
+        self._q_n = q + 1
+        if self._q_n == self._qcap:
+            self._launch_queue()
+
+    def _launch_queue(self):
+        n = self._q_n
+        if n == 0:
+            return
+        torch = self._torch
+        L = self._h.L
+        st = self._stage[self._q_buf]
+        capi.check(L.tslam_tsdf_integrate_depth(self._h.h, capi.C.c_void_p(st.data_ptr()), capi.MEM_HOST, n,
+                                                self._stage_shape[0], self._stage_shape[1], capi.np_ptr(self._q_R),
+                                                capi.np_ptr(self._q_T), capi.np_ptr(self._q_s), capi.F_COMMIT,
+                                                capi.stream_ptr()))
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_ev[self._q_buf] = ev
+        self._q_buf ^= 1
+        self._q_n = 0
+
+    def _flush(self):
+        self._launch_queue()
+
+    def recast_pcl_to_map(self, R, T, xyz_array, rgb_array):
+        """:157-160.  xyz_array [n,3] (any float dtype; computed in f32 like the kernel's ti.f32 cast, :171-174)."""
+        self._flush()
+        self.set_pose(R, T)
+        xyz = np.ascontiguousarray(np.asarray(xyz_array, dtype=np.float32).reshape(-1, 3))
+        s = 0 if self.is_global_map else self.active_submap_id[None]
+        self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=s, commit=True)
+        self._torch.cuda.current_stream().synchronize()  # pageable source
+
+    # ------------------------------------------------------------------ submaps / fusion (:272-318)
+    def reset(self):
+        self._q_n = 0
+        self._h.reset()
+
+    def fuse_submaps(self, submaps):
+        submaps._flush()
+        t = time.time()
+        self._q_n = 0
+        self._h.fuse_from(submaps._h)
+        print(f"[DenseTSDF] Fuse submaps {(time.time() - t) * 1000:.1f}ms, active local: {submaps.active_submap_id[None]} "
+              f"remote: {submaps.remote_submap_num[None]}")
+
+    # ------------------------------------------------------------------ exporters (:320-389)
+    def _active(self):
+        return 0 if self.is_global_map else self.active_submap_id[None]
+
+    def cvt_occupy_to_voxels(self):
+        self.cvt_TSDF_surface_to_voxels()
+
+    def cvt_TSDF_surface_to_voxels(self):
+        self._flush()
+        self.num_TSDF_particles.t.zero_()  # add_to_cur=False (:342-343)
+        self._h.extract_surface(self._active(), self.export_TSDF_xyz.t, self.export_color.t, self.num_TSDF_particles.t)
+
+    def cvt_TSDF_surface_to_voxels_to(self, num_TSDF_particles, max_disp_particles, export_TSDF_xyz, export_color):
+        self._flush()
+        xyz = export_TSDF_xyz.t[:max_disp_particles]
+        rgb = export_color.t[:max_disp_particles]
+        self._h.extract_surface(self._active(), xyz, rgb, num_TSDF_particles.t)
+
+    def cvt_TSDF_to_voxels_slice(self, z, dz=0.5, clear_last=True):
+        self._flush()
+        if clear_last:
+            self.num_TSDF_particles.t.zero_()
+        self._h.extract_slice(self._active(), z, dz, self.export_TSDF_xyz.t, self.export_TSDF.t, self.export_color.t,
+                              self.num_TSDF_particles.t)
+
+    def get_voxels_TSDF_surface(self):
+        self.cvt_TSDF_surface_to_voxels()
+        return self.export_TSDF_xyz.to_numpy(), self.export_TSDF.to_numpy(), None
+
+    def get_voxels_TSDF_slice(self, z):
+        self.cvt_TSDF_to_voxels_slice(z)
+        return self.export_TSDF_xyz.to_numpy(), self.export_TSDF.to_numpy()
+
+    def get_voxels_occupy(self):
+        self.cvt_occupy_to_voxels()
+        return self.export_TSDF_xyz.to_numpy(), self.export_color.to_numpy()
+
+    def finalization_current_submap(self):
+        self._flush()
+
+    # ------------------------------------------------------------------ I/O (:412-515)
+    def count_active(self):
+        self._flush()
+        return self._h.count_active(self._active())
+
+    def to_numpy(self, data_indices, data_tsdf, data_wtsdf, data_occ, data_color):
+        """Fill caller arrays (dtypes of export_submap, :459-462) with the observed voxels of the active submap."""
+        self._flush()
+        idx, t, w, occ = self._h.gather(self._active())
+        n = idx.shape[0]
+        data_indices[:n] = idx
+        data_tsdf[:n] = t
+        data_wtsdf[:n] = w
+        data_occ[:n] = occ
+
+    def load_numpy(self, submap_id, data_indices, data_tsdf, data_wtsdf, data_occ, data_color):
+        self._flush()
+        occ = np.clip(np.asarray(data_occ).astype(np.int64), -128, 127).astype(np.int8)
+        self._h.scatter(submap_id, np.asarray(data_indices).astype(np.int32), np.asarray(data_tsdf, dtype=np.float32),
+                        np.asarray(data_wtsdf, dtype=np.float32), occ)
+
+    def export_submap(self):
+        s = time.time()
+        num = self.count_active()
+        indices = np.zeros((num, 3), np.int16)
+        tsdf = np.zeros((num), np.float16)
+        w_tsdf = np.zeros((num), np.float16)
+        occupy = np.zeros((num), np.int8)
+        color = np.array([])
+        self.to_numpy(indices, tsdf, w_tsdf, occupy, color)
+        obj = {
+            'indices': indices,
+            'TSDF': tsdf,
+            'W_TSDF': w_tsdf,
+            'color': color,
+            'occupy': occupy,
+            "map_scale": [self.map_size_xy, self.map_size_z],
+            "voxel_scale": self.voxel_scale,
+            "texture_enabled": self.enable_texture,
+            "num_voxel_per_blk_axis": self.num_voxel_per_blk_axis,
+        }
+        print(f"Export submap {self.active_submap_id[None]} to numpy, voxels {num / 1024:.1f}k, time: {1000 * (time.time() - s):.1f}ms")
+        return obj
+
+    def saveMap(self, filename):
+        np.save(filename, self.export_submap())
+
+    @staticmethod
+    def loadMap(filename):
+        obj = np.load(filename, allow_pickle=True).item()
+        vs = obj['voxel_scale'] if 'voxel_scale' in obj else obj['voxel_size']  # shipped fixtures carry the legacy key
+        mapping = DenseTSDF(map_scale=obj['map_scale'], voxel_scale=float(vs), texture_enabled=obj['texture_enabled'],
+                            num_voxel_per_blk_axis=obj['num_voxel_per_blk_axis'], is_global_map=True)
+        mapping.load_numpy(0, obj['indices'], obj['TSDF'], obj['W_TSDF'], obj['occupy'], obj['color'])
+        print(f"[SubmapMapping] Loaded {obj['TSDF'].shape[0]} voxels from {filename}")
+        return mapping
+
+    def input_remote_submap(self, submap):
+        # remote submaps fill the table from the top (:500-515)
+        self.remote_submap_num[None] = self.remote_submap_num[None] + 1
+        idx = self.max_submap_num - self.remote_submap_num[None]
+        R, T = submap['pose']
+        self.load_numpy(idx, submap['indices'], submap['TSDF'], submap['W_TSDF'], submap['occupy'], np.array([]))
+        self.set_base_pose_submap(idx, R, T)
+        return idx
+
+    # ------------------------------------------------------------------ extras (not in the reference)
+    def frame_counters(self):
+        """Flush, commit and read the integrate counters back (bench.py end-to-end arm)."""
+        self._flush()
+        st = self._h.stats()
+        st["d2h_bytes"] = 8 * 8 + 5 * 8 + 4 * 4
+        return st
+
+    def esdf_update(self):
+        """Converged ESDF of the active submap (DenseSDF.propogate_esdf semantics, dense_esdf.py:302-333)."""
+        self._flush()
+        return self._h.esdf_update(self._active())
+
+    def get_voxels_ESDF(self):
+        return self._h.esdf_gather(self._active())

@@ -1,0 +1,91 @@
+"""BaseMap - host-side pose state shared by the map classes.
+
+Mirrors the reference's BaseMap (taichi_slam/mapping/mapping_common.py) for everything the
+callers use from Python: pose plumbing (set_pose / set_base_pose / convert_by_base, :91-100,
+:141-156), the submap pose tables (:102-131) and the camera-intrinsic setters (:25-29).  The
+device-side helpers of the reference (coordinate transforms, unprojection, :31-58, :221-266) live
+inside the CUDA kernels of libtslam.so.
+"""
+import numpy as np
+
+from .field import HostScalar
+
+
+def sign(val):  # mapping_common.py:5-7
+    return (0 < val) - (val < 0)
+
+
+class BaseMap:
+    def __init__(self, voxel_scale):
+        self.base_T_np = np.zeros(3)          # :16-17
+        self.base_R_np = np.eye(3)
+        self.input_R_np = np.eye(3, dtype=np.float32)   # input_R / input_T 0-d fields (:12-13), kept on the host
+        self.input_T_np = np.zeros(3, dtype=np.float32)
+        self.frame_id = 0
+        self.submap_enabled = False
+        self.voxel_scale = voxel_scale
+        self.voxel_scale_ = np.array([voxel_scale] * 3, dtype=np.float32)  # :23
+        self.K_cam_dep = None
+        self.K_cam_color = None
+
+    # :25-29
+    def set_dep_camera_intrinsic(self, K):
+        self.K_cam_dep = [float(k) for k in np.asarray(K).reshape(-1)]
+        self._on_intrinsics()
+
+    def set_color_camera_intrinsic(self, K):
+        self.K_cam_color = [float(k) for k in np.asarray(K).reshape(-1)]
+
+    def _on_intrinsics(self):
+        pass
+
+    # :91-100
+    def convert_by_base(self, R, T):
+        R = np.asarray(R, dtype=np.float64)
+        T = np.asarray(T, dtype=np.float64)
+        if self.submap_enabled:
+            sid = self.active_submap_id[None]
+            base_R_inv = self.submaps_base_R_np[sid].T
+            R_ = base_R_inv @ R
+            T_ = base_R_inv @ (T - self.submaps_base_T_np[sid])
+        else:
+            base_R_inv = self.base_R_np.T
+            R_ = base_R_inv @ R
+            T_ = base_R_inv @ (T - self.base_T_np)
+        return R_, T_
+
+    # :102-111
+    def initialize_submap_fields(self, max_submap_num):
+        self.submap_enabled = True
+        self.submaps_base_R_np = np.zeros((max_submap_num, 3, 3))
+        self.submaps_base_T_np = np.zeros((max_submap_num, 3))
+        self.active_submap_id = HostScalar(0)
+        self.remote_submap_num = HostScalar(0)
+
+    def get_active_submap_id(self):  # :113-114
+        return self.active_submap_id[None]
+
+    def switch_to_next_submap(self):  # :116-119
+        self.finalization_current_submap()
+        self.active_submap_id[None] += 1
+        return self.active_submap_id[None]
+
+    def finalization_current_submap(self):
+        pass
+
+    def set_base_pose_submap(self, submap_id, _R, _T):  # :121-131
+        self.submaps_base_T_np[submap_id] = _T
+        self.submaps_base_R_np[submap_id] = _R
+        self._upload_submap_pose(int(submap_id), np.asarray(_R, dtype=np.float64), np.asarray(_T, dtype=np.float64))
+
+    def _upload_submap_pose(self, submap_id, R, T):
+        raise NotImplementedError
+
+    def set_base_pose(self, _R, _T):  # :141-147
+        self.base_T_np = np.asarray(_T, dtype=np.float64)
+        self.base_R_np = np.asarray(_R, dtype=np.float64)
+
+    def set_pose(self, _R, _T):  # :149-156
+        _R, _T = self.convert_by_base(_R, _T)
+        self.input_R_np = _R.astype(np.float32)
+        self.input_T_np = _T.astype(np.float32)

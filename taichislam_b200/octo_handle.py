@@ -41,6 +41,9 @@ class OctoHandle:
         R, T = capi.f32c(R).reshape(9), capi.f32c(T).reshape(3)
         capi.check(self.L.tslam_octo_set_submap_pose(self.h, int(s), capi.np_ptr(R), capi.np_ptr(T)))
 
+    def set_intrinsics(self, K9):
+        capi.check(self.L.tslam_octo_set_intrinsics(self.h, K9[0], K9[4], K9[2], K9[5]))
+
     def integrate_points(self, xyz, R, T, submap=0):
         torch = self.torch
         if isinstance(xyz, torch.Tensor):

@@ -21,10 +21,11 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 def make_pair(map_scale, **kw):
     from oracle.oracle import OracleTSDF
     from taichislam_b200.tsdf_handle import TsdfHandle
+    gpu_only = {k: kw.pop(k) for k in ("max_submaps", "max_blocks", "max_image_pixels", "max_points") if k in kw}
     o = OracleTSDF(map_scale=map_scale, K=syn.K_DEPTH, **kw)
     okw = dict(kw)
     okw.pop("num_voxel_per_blk_axis", None)
-    g = TsdfHandle(o.N, o.Nz, K=syn.K_DEPTH, **okw)
+    g = TsdfHandle(o.N, o.Nz, K=syn.K_DEPTH, **okw, **gpu_only)
     return g, o
 
 

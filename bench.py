@@ -271,27 +271,31 @@ def main():
             from taichislam_b200.mapping import DenseTSDF
             m = DenseTSDF(map_scale=MAP_SCALE, voxel_scale=0.05, num_voxel_per_blk_axis=16, is_global_map=True)
             m.set_dep_camera_intrinsic(syn.K_DEPTH)
+            m.set_base_pose_submap(0, np.eye(3), np.zeros(3))  # pose-table rows start at zero (mapping_common.py:106-107)
             host = torch.from_numpy(np.ascontiguousarray(make_inputs(BATCH, 0)[0]).view(np.int16)).pin_memory()
             host_np = host.numpy().view(np.uint16)
             empty_tex = np.array([])
             t = rank * 100000 + 50000
+            eRs, eTs = syn.stream_poses(n_steps_total * BATCH, start=t)   # host pose stream prepared up front
+            ek = [0]
 
-            def step_e2e(t):
-                _, Rs, Ts = make_inputs(BATCH, t)
+            def step_e2e():
+                k0 = ek[0]
+                ek[0] += BATCH
                 for q in range(BATCH):
-                    m.recast_depth_to_map(Rs[q], Ts[q], host_np[q], empty_tex)
+                    m.recast_depth_to_map(eRs[k0 + q], eTs[k0 + q], host_np[q], empty_tex)
                 return m.frame_counters()  # flushes the queue, commits, D2H read of the integrate counters
 
             for i in range(args.warmup):
-                step_e2e(t)
-                t += BATCH
+                step_e2e()
+            m.frame_counters()
             barrier()
             t0 = time.perf_counter()
             for i in range(args.steps):
-                res = step_e2e(t)
-                t += BATCH
+                res = step_e2e()
             barrier()
             dt = time.perf_counter() - t0
+            assert res["n_updates"] > 0, "e2e arm integrated nothing"
             tm = torch.tensor([dt], device="cuda", dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)

@@ -95,7 +95,7 @@ struct KeyHash {
 // (dense_esdf.py:88-92).
 struct Block {
   float T[OB3], W[OB3];
-  float A[OB3], Bw[OB3];  // pending sum(w*d), sum(w)  (canonical mode)
+  double A[OB3], Bw[OB3];  // pending sum(w*d), sum(w) (canonical mode): EXACT-ish double sums of the f32 terms, order independent
   uint8_t obs[OB3];
   int occ[OB3];           // i8 in the reference (dense_tsdf.py:95); wider here, saturated on export
   float esdf[OB3];
@@ -302,8 +302,8 @@ static void raymarch(Tsdf& m, BucketGrid& g, const float Tin[3], int s) {
       int o; Block* b = m.touch(s, xi, yi, zi, &o);
       if (mode == MODE_CANONICAL) {
         if (!b->pending) { b->pending = true; m.dirty.push_back(b); }
-        b->A[o] += w * ds;
-        b->Bw[o] += w;
+        b->A[o] += (double)(w * ds);
+        b->Bw[o] += (double)w;
       } else if (mode == MODE_F32_LITERAL) {
         float T0 = b->T[o], W0 = b->W[o];
         b->T[o] = (T0 * W0 + w * ds) / (W0 + w);  // :264
@@ -325,10 +325,11 @@ static void commit(Tsdf& m, bool clamp) {
   for (Block* b : m.dirty) {
     b->pending = false;
     for (int o = 0; o < OB3; o++) {
-      if (b->Bw[o] > 0.0f) {
+      if (b->Bw[o] > 0.0) {
         float T0 = b->T[o], W0 = b->W[o];
-        float Wn = W0 + b->Bw[o];
-        b->T[o] = (T0 * W0 + b->A[o]) / Wn;
+        const float Af = (float)b->A[o], Bf = (float)b->Bw[o];  // exact sums, rounded once
+        float Wn = W0 + Bf;
+        b->T[o] = (T0 * W0 + Af) / Wn;
         b->W[o] = clamp ? fminf(Wn, WMAX) : Wn;
         b->obs[o] = 1;
         b->A[o] = 0.0f;

@@ -138,13 +138,22 @@ __device__ __forceinline__ int ts_get_or_alloc(const G& g, unsigned long long ke
   return -1;
 }
 
-__device__ __forceinline__ void ts_mark_dirty(const TsGrid& g, int blk) {
-  if (*(volatile int*)&g.dirty_flag[blk] == 0) {
-    if (atomicExch(&g.dirty_flag[blk], 1) == 0) {
-      int p = atomicAdd(g.n_dirty, 1);
-      g.dirty_list[p] = blk;
-    }
+// Touched blocks are flagged with a fire-and-forget store (no load on the ray-march critical
+// path); k_collect_dirty compacts the flags into dirty_list before a commit.
+__device__ __forceinline__ void ts_mark_dirty(const TsGrid& g, int blk) { g.dirty_flag[blk] = 1; }
+
+// Fast lookup for the hot loops: first probe through L1 (plain cached load).  Entries are only
+// ever inserted while kernels run (the table is cleared between launches, where L1 is
+// invalidated), so a cached hit is always valid; anything else falls back to the coherent path.
+template <class G>
+__device__ __forceinline__ int ts_get_or_alloc_cached(const G& g, unsigned long long key) {
+  const uint32_t slot = ts_hash(key) & g.table_mask;
+  const unsigned long long cur = __ldca(&g.table[slot]);
+  if ((cur >> 24) == key) {
+    const unsigned idx = (unsigned)(cur & TS_IDX_MASK);
+    if (idx < TS_IDX_OVERFLOW) return (int)idx;
   }
+  return ts_get_or_alloc(g, key);
 }
 
 // ---------------------------------------------------------------------------

@@ -54,26 +54,53 @@ __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz)
 }
 
 __device__ __forceinline__ void red_add_f32x2(float2* addr, float a, float b) {
-  // one 8-byte vector reduction: REDG.E.ADD.F32x2 (sm_90+)
-  atomicAdd(addr, make_float2(a, b));
+  // one 8-byte vector reduction without return value: REDG.E.ADD.F32x2 (sm_90+).  Spelled in PTX because
+  // atomicAdd(float2*) was lowered to ATOMG (response sector per update) inside the divergent march loop.
+  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
-// accumulate one unprojected point into its frame's bucket table.
-// process_point (dense_tsdf.py:227-234) with exact fixed-point sums.
-__device__ __forceinline__ void bucket_accumulate(TsBucket* tab, uint32_t cap_mask, uint32_t tab_base, float px, float py,
-                                                  float pz, float dep, float vs, uint32_t* ray_list, int* n_rays,
+__device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u32(unsigned int* addr, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+// accumulate one unprojected point per lane into the frame's bucket table.
+// process_point (dense_tsdf.py:227-234) with exact fixed-point sums.  Lanes of a warp that fall into
+// the same bucket (neighbouring pixels usually do) are merged first (match.any + redux): one probe and
+// one set of reductions per distinct bucket per warp instead of per pixel.  Must be called by all 32
+// lanes; `valid` masks lanes without a point.
+__device__ __forceinline__ void bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, uint32_t tab_base, float px, float py,
+                                                  float pz, float dep, float vs, bool agg_ok, uint32_t* ray_list, int* n_rays,
                                                   uint32_t ray_cap, int* err) {
-  int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
-  unsigned long long key = bucket_key(bx, by, bz);
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
+  const unsigned long long key = bucket_key(bx, by, bz);
+  long long qx = __float2ll_rn(px * FIXQ), qy = __float2ll_rn(py * FIXQ), qz = __float2ll_rn(pz * FIXQ), qd = __float2ll_rn(dep * FIXQ);
+  int cnt = 1;
+  if (agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
+    const unsigned grp = __match_any_sync(vmask, key);
+    const bool leader = (threadIdx.x & 31) == (__ffs(grp) - 1);
+    cnt = __popc(grp);
+    if (cnt > 1) {
+      qx = (long long)__reduce_add_sync(grp, (int)qx);
+      qy = (long long)__reduce_add_sync(grp, (int)qy);
+      qz = (long long)__reduce_add_sync(grp, (int)qz);
+      qd = (long long)__reduce_add_sync(grp, (int)qd);
+    }
+    if (!leader) return;
+  }
   uint32_t h = ts_hash(key) & cap_mask;
   TsBucket* b = nullptr;
   for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
     TsBucket* c = &tab[h];
     unsigned long long cur = ts_ld_volatile(&c->key);
     if (cur == 0ull) {
-      unsigned long long prev = atomicCAS(&c->key, 0ull, key);
+      const unsigned long long prev = atomicCAS(&c->key, 0ull, key);
       if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
-        uint32_t p = (uint32_t)atomicAdd(n_rays, 1);
+        const uint32_t p = (uint32_t)atomicAdd(n_rays, 1);
         if (p < ray_cap) ray_list[p] = tab_base + h; else atomicOr(err, TS_ERR_RAYLIST_FULL);
         b = c;
         break;
@@ -84,71 +111,73 @@ __device__ __forceinline__ void bucket_accumulate(TsBucket* tab, uint32_t cap_ma
     h = (h + 1) & cap_mask;
   }
   if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return; }
-  atomicAdd(&b->cnt, 1);
-  atomicAdd((unsigned long long*)&b->sx, (unsigned long long)__float2ll_rn(px * FIXQ));
-  atomicAdd((unsigned long long*)&b->sy, (unsigned long long)__float2ll_rn(py * FIXQ));
-  atomicAdd((unsigned long long*)&b->sz, (unsigned long long)__float2ll_rn(pz * FIXQ));
-  atomicAdd((unsigned long long*)&b->sd, (unsigned long long)__float2ll_rn(dep * FIXQ));
+  red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
+  red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
+  red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
+  red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
+  red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
 }
 
 // ---------------------------------------------------------------------------
 // K1a: depth frames -> per-frame buckets.
 // recast_depth_to_map_kernel phase 1 (dense_tsdf.py:188-213) + unproject_point_dep
 // (mapping_common.py:31-41).  One thread per SAMPLED pixel (the reference walks a
-// row per thread, :192-194), blockIdx.y = frame of the batch.
+// row per thread, :192-194); a warp covers an 8x4 tile of sampled pixels, a CTA 32x8;
+// blockIdx.z = frame of the batch.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int h, int w, int hh, int ww,
-                                                       const __grid_constant__ TsBatch batch, TsIntrin in,
+                                                       const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
                                                        TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
                                                        int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
-  const int f = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.z;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ii = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
+  const int jj = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
   bool valid = false;
-  if (t < hh * ww) {
-    const int jj = t / ww, ii = t - jj * ww;
+  float px = 0.f, py = 0.f, pz = 0.f, dep = 0.f;
+  if (ii < ww && jj < hh) {
     const int j = jj * in.step, i = ii * in.step;
     const uint16_t d = depth[(size_t)f * h * w + (size_t)j * w + i];
     const float df = (float)d;
     if (d != 0 && !(df > in.dmax_mm || df < in.dmin_mm)) {  // :196-199
       valid = true;
-      const float dep = df / 1000.0f;                        // :201
+      dep = df / 1000.0f;                                    // :201
       const float x = ((float)i - in.cx) * dep / in.fx;     // mapping_common.py:37-40
       const float y = ((float)j - in.cy) * dep / in.fy;
       const TsFrame& fr = batch.f[f];
-      const float px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * dep;  // :203 input_R @ pt (rotation only)
-      const float py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * dep;
-      const float pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * dep;
-      bucket_accumulate(buckets + (size_t)f * bucket_cap, bucket_cap - 1, (uint32_t)f * bucket_cap, px, py, pz, dep, in.vs,
-                        ray_list, n_rays, ray_cap, err);
+      px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * dep;     // :203 input_R @ pt (rotation only)
+      py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * dep;
+      pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * dep;
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  if ((threadIdx.x & 31) == 0) {
+  bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, (uint32_t)f * bucket_cap, px, py, pz, dep, in.vs,
+                    agg_ok != 0, ray_list, n_rays, ray_cap, err);
+  if (lane == 0) {
     if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
   }
 }
 
 // K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
 __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
-                                                        TsIntrin in, TsBucket* buckets, uint32_t bucket_cap,
+                                                        TsIntrin in, int agg_ok, TsBucket* buckets, uint32_t bucket_cap,
                                                         uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
                                                         int* err) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = false;
+  float px = 0.f, py = 0.f, pz = 0.f, len = 0.f;
   if (t < n) {
     const float x = xyz[3 * (size_t)t], y = xyz[3 * (size_t)t + 1], z = xyz[3 * (size_t)t + 2];
     const TsFrame& fr = batch.f[0];
-    const float px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * z;  // :175
-    const float py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * z;
-    const float pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * z;
-    const float len = sqrtf((px * px + py * py) + pz * pz);       // :176
-    if (len < in.max_ray) {                                       // :177
-      valid = true;
-      bucket_accumulate(buckets, bucket_cap - 1, 0u, px, py, pz, len, in.vs, ray_list, n_rays, ray_cap, err);  // :185
-    }
+    px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * z;  // :175
+    py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * z;
+    pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * z;
+    len = sqrtf((px * px + py * py) + pz * pz);       // :176
+    valid = len < in.max_ray;                          // :177
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
+  bucket_accumulate(valid, buckets, bucket_cap - 1, 0u, px, py, pz, len, in.vs, agg_ok != 0, ray_list, n_rays, ray_cap, err);  // :185
   if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
@@ -164,65 +193,85 @@ __global__ void __launch_bounds__(128) k_raymarch(const __grid_constant__ TsBatc
                                                    const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
   const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
   const float vs = in.vs;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   unsigned int my_updates = 0, my_oob = 0, my_rays = 0;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += gridDim.x * blockDim.x) {
-    const uint32_t id = ray_list[r];
-    const uint32_t f = id >> bucket_shift;
-    TsBucket* bk = &buckets[id];
-    const int cnt = bk->cnt;
-    const long long sx = bk->sx, sy = bk->sy, sz = bk->sz, sd = bk->sd;
-    {  // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
-      uint4 z4 = make_uint4(0, 0, 0, 0);
+  // control flow is kept WARP-UNIFORM (32 consecutive rays per warp, march to the longest ray, predicated
+  // lanes) so that the one reduction per step is issued once for all active lanes.
+  for (uint32_t base = warp0 * 32u; base < n_rays; base += n_warps * 32u) {
+    const uint32_t r = base + lane;
+    bool live = r < n_rays;
+    int cnt = 0, s = 0, n = 0;
+    long long sx = 0, sy = 0, sz = 0, sd = 0;
+    uint32_t f = 0;
+    if (live) {
+      const uint32_t id = ray_list[r];
+      f = id >> bucket_shift;
+      TsBucket* bk = &buckets[id];
+      cnt = bk->cnt;
+      sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
+      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
       uint4* q = reinterpret_cast<uint4*>(bk);
       q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
+      live = cnt > 0;  // :240
     }
-    if (cnt <= 0) continue;  // :240
-    my_rays++;
-    const TsFrame& fr = batch.f[f];
-    const int s = fr.submap;
-    const double den = (double)cnt * FIXQ_D;
-    const float mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
-    const float my = (float)((double)sy / den);
-    const float mz = (float)((double)sz / den);
-    const float zc = (float)((double)sd / den);  // z = new_pcl_z/c (:247)
-    const float L = sqrtf((mx * mx + my * my) + mz * mz);  // :244
-    if (!(L > 0.0f)) continue;
-    const float ux = mx / L, uy = my / L, uz = mz / L;  // :245
-    const float Tx = fr.T[0], Ty = fr.T[1], Tz = fr.T[2];
-    const float Px = mx + Tx, Py = my + Ty, Pz = mz + Tz;  // :246
+    float mx = 0.f, my = 0.f, mz = 0.f, ux = 0.f, uy = 0.f, uz = 0.f, Tx = 0.f, Ty = 0.f, Tz = 0.f, Px = 0.f, Py = 0.f, Pz = 0.f,
+          wgt = 0.f;
     unsigned long long cur_key = TS_EMPTY;
     int cur_blk = -1;
-    {  // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
-      const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
-      if (ts_in_bounds(g, oi, oj, ok)) {
-        cur_key = ts_pack_key(s, oi >> TS_BSHIFT, oj >> TS_BSHIFT, ok >> TS_BSHIFT);
-        cur_blk = ts_get_or_alloc(g, cur_key);
-        if (cur_blk >= 0) {
-          g.occ[(size_t)cur_blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
-          ts_mark_dirty(g, cur_blk);  // touched blocks are listed even when only `occupy` changed
+    if (live) {
+      my_rays++;
+      const TsFrame& fr = batch.f[f];
+      s = fr.submap;
+      const double den = (double)cnt * FIXQ_D;
+      mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
+      my = (float)((double)sy / den);
+      mz = (float)((double)sz / den);
+      const float zc = (float)((double)sd / den);  // z = new_pcl_z/c (:247)
+      const float L = sqrtf((mx * mx + my * my) + mz * mz);  // :244
+      if (L > 0.0f) {
+        ux = mx / L; uy = my / L; uz = mz / L;  // :245
+        Tx = fr.T[0]; Ty = fr.T[1]; Tz = fr.T[2];
+        Px = mx + Tx; Py = my + Ty; Pz = mz + Tz;  // :246
+        // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
+        const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
+        if (ts_in_bounds(g, oi, oj, ok)) {
+          cur_key = ts_pack_key(s, oi >> TS_BSHIFT, oj >> TS_BSHIFT, ok >> TS_BSHIFT);
+          cur_blk = ts_get_or_alloc_cached(g, cur_key);
+          if (cur_blk >= 0) {
+            g.occ[(size_t)cur_blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
+            ts_mark_dirty(g, cur_blk);  // touched blocks are listed even when only `occupy` changed
+          }
         }
+        n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
+        wgt = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
       }
     }
-    const int n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
-    const float wgt = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
     float jf = 0.0f;
-    for (int it = 0; it < n; ++it) {
+    for (int it = 0; it < nmax; ++it) {
       jf += 1.0f;  // :252
       const float x = (ux * jf) * vs + Tx, y = (uy * jf) * vs + Ty, z = (uz * jf) * vs + Tz;  // :253
       const int xi = iroundf(x / vs), yi = iroundf(y / vs), zi = iroundf(z / vs);           // :254
       const float vx = Px - x, vy = Py - y, vz = Pz - z;                                      // :258
       const float d = sqrtf((vx * vx + vy * vy) + vz * vz);                                  // :259
       const float ds = d * sgnf((vx * mx + vy * my) + vz * mz);                              // :260
-      if (!ts_in_bounds(g, xi, yi, zi)) { my_oob++; continue; }
+      const bool stepping = it < n;
+      const bool inb = stepping && ts_in_bounds(g, xi, yi, zi);
+      my_oob += (stepping && !inb) ? 1u : 0u;
       const unsigned long long key = ts_pack_key(s, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
-      if (key != cur_key) {
+      if (inb && key != cur_key) {  // block boundary crossed: ~ every 10th step of a lane
         cur_key = key;
-        cur_blk = ts_get_or_alloc(g, key);
+        cur_blk = ts_get_or_alloc_cached(g, key);
         if (cur_blk >= 0) ts_mark_dirty(g, cur_blk);
       }
-      if (cur_blk < 0) continue;  // pool exhausted (error flag raised)
-      red_add_f32x2(&g.acc[(size_t)cur_blk * TS_B3 + ts_voxel_off(xi, yi, zi)], wgt * ds, wgt);  // :264,:267
-      my_updates++;
+      __syncwarp();
+      if (inb && cur_blk >= 0) {  // cur_blk < 0: pool exhausted (error flag raised)
+        red_add_f32x2(&g.acc[(size_t)cur_blk * TS_B3 + ts_voxel_off(xi, yi, zi)], wgt * ds, wgt);  // :264,:267
+        my_updates++;
+      }
     }
   }
   // statistics: one atomic per warp
@@ -231,7 +280,7 @@ __global__ void __launch_bounds__(128) k_raymarch(const __grid_constant__ TsBatc
     my_oob += __shfl_xor_sync(0xffffffffu, my_oob, o);
     my_rays += __shfl_xor_sync(0xffffffffu, my_rays, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     if (my_updates) atomicAdd(&ctr->n_updates, (unsigned long long)my_updates);
     if (my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
     if (my_rays) atomicAdd(&ctr->n_rays, (unsigned long long)my_rays);
@@ -268,6 +317,23 @@ __global__ void __launch_bounds__(256) k_commit(TsGrid g, int clamp, int fused_o
       }
     }
     if (threadIdx.x == 0) g.dirty_flag[blk] = 0;
+  }
+}
+// compact the per-block dirty flags into dirty_list (warp-aggregated append)
+__global__ void __launch_bounds__(256) k_collect_dirty(TsGrid g) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  const int stride = gridDim.x * blockDim.x;
+  const int iters = (nb + stride - 1) / stride;
+  for (int it = 0; it < iters; ++it) {
+    const int b = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool want = b < nb && g.dirty_flag[b] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) continue;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(g.n_dirty, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) g.dirty_list[base + __popc(m & ((1u << lane) - 1))] = b;
   }
 }
 __global__ void k_reset_counters(int* a, int* b) {
@@ -467,6 +533,8 @@ extern "C" int tslam_tsdf_set_submap_pose(tslam_tsdf_t* m, int32_t s, const floa
 // ---------------------------------------------------------------------------
 static int ts_launch_commit(tslam_tsdf* m, cudaStream_t st, int clamp, int fused) {
   int grid = m->sm_count * 8;
+  k_collect_dirty<<<(m->g.max_blocks + 255) / 256 < m->sm_count * 4 ? (m->g.max_blocks + 255) / 256 : m->sm_count * 4, 256, 0, st>>>(m->g);
+  TS_LAUNCH_CHECK(m);
   k_commit<<<grid, 256, 0, st>>>(m->g, clamp, fused);
   TS_LAUNCH_CHECK(m);
   k_reset_counters<<<1, 1, 0, st>>>(m->g.n_dirty, nullptr);
@@ -532,9 +600,10 @@ extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth
     }
     cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
-    dim3 grid1((hh * ww + 255) / 256, nf);
-    k_bucket_depth<<<grid1, 256, 0, st>>>(src, h, w, hh, ww, batch, m->in, m->buckets, m->bucket_cap, m->ray_list, m->n_rays,
-                                          m->ray_list_cap, m->counters, m->g.err);
+    dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
+    const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
+    k_bucket_depth<<<grid1, 256, 0, st>>>(src, h, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
+                                          m->n_rays, m->ray_list_cap, m->counters, m->g.err);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
     k_raymarch<<<m->sm_count * 16, 128, 0, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays, m->ray_list_cap,
@@ -571,7 +640,8 @@ extern "C" int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, in
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
   cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
-  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, m->buckets, cap_total, m->ray_list, m->n_rays,
+  const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
+  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
                                                     m->ray_list_cap, m->counters, m->g.err);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
@@ -870,7 +940,7 @@ __global__ void __launch_bounds__(256) k_fuse(TsGrid dst, TsGrid src, const floa
         const unsigned long long key = ts_pack_key(0, ci >> TS_BSHIFT, cj >> TS_BSHIFT, ck >> TS_BSHIFT);
         if (key != cur_key) {
           cur_key = key;
-          cur_blk = ts_get_or_alloc(dst, key);
+          cur_blk = ts_get_or_alloc_cached(dst, key);
           if (cur_blk >= 0) ts_mark_dirty(dst, cur_blk);
         }
         if (cur_blk < 0) continue;

@@ -33,7 +33,9 @@ def test_dense_tsdf_per_frame_api_matches_oracle():
     m.set_dep_camera_intrinsic(syn.K_DEPTH)
     o = OracleTSDF(K=syn.K_DEPTH, **kw)
     base_R, base_T = rot_xyz(0.0, 0.0, 0.3), np.array([1.0, -0.5, 0.2])
-    m.set_base_pose(base_R, base_T)
+    # DenseTSDF always enables the submap pose table (dense_tsdf.py:80 -> mapping_common.py:102-103), whose rows start
+    # at ZERO: like the reference, poses are meaningless until the active submap's base pose is set.
+    m.set_base_pose_submap(0, base_R, base_T)
     d = syn.scene_room()
     n = 70  # crosses the 64-frame queue boundary
     for q in range(n):

@@ -60,21 +60,30 @@ def test_single_frame_generic_pose_512(scene):
 
 
 def test_stream_batch_equals_sequential_frames():
-    """12 frames of the bench stream: one batched call (commit once) vs the oracle committing every frame."""
+    """12 frames of the bench stream.  (a) one batched call, committed once == oracle accumulating the 12 frames and
+    committing once; (b) frame-by-frame calls with a commit each == oracle committing every frame; (c) the two
+    granularities agree wherever the Wmax=1000 clamp never bound (W < 1000): the only place commit granularity can
+    matter (dense_tsdf.py:267)."""
     n = 12
     d = np.stack([syn.scene_sphere(4.0)] * n)
     Rs, Ts = syn.stream_poses(n, start=5)
     g, o = make_pair([25.6, 25.6], is_global_map=True)
     g.integrate_depth(d, Rs, Ts)
     for q in range(n):
-        o.integrate_depth(Rs[q], Ts[q], d[q], commit=True)
+        o.integrate_depth(Rs[q], Ts[q], d[q], commit=(q == n - 1))
     stats_equal(g, o)
     compare_voxels(g.gather(), o.gather(), TOL)
-    # and frame-by-frame calls with a commit each give the same map
-    g2, _ = make_pair([25.6, 25.6], is_global_map=True)
+    g2, o2 = make_pair([25.6, 25.6], is_global_map=True)
     for q in range(n):
         g2.integrate_depth(d[q], Rs[q][None], Ts[q][None], commit=True)
-    compare_voxels(g2.gather(), o.gather(), TOL)
+        o2.integrate_depth(Rs[q], Ts[q], d[q], commit=True)
+    compare_voxels(g2.gather(), o2.gather(), TOL)
+    i1, t1, w1, _ = as_dict_rows(*g.gather())
+    i2, t2, w2, _ = as_dict_rows(*g2.gather())
+    assert np.array_equal(i1, i2)
+    free = (w1 < 999.0) & (w2 < 999.0)
+    assert free.mean() > 0.9
+    assert np.abs(t1[free] - t2[free]).max() <= TOL and np.all(np.abs(w1[free] - w2[free]) <= 1e-4 * np.maximum(1, w1[free]))
 
 
 def test_device_resident_input_and_uncommitted_reads():
@@ -155,7 +164,7 @@ def test_surface_and_slice_export():
     d = syn.scene_room()
     R = rot_xyz(0.0, 0.2, 0.1)
     T = np.array([0.0, 0.0, 0.4])
-    g, o = make_pair([25.6, 25.6], is_global_map=True, disp_floor=-1.0, disp_ceiling=2.5)
+    g, o = make_pair([25.6, 25.6], is_global_map=True, disp_floor=-2.0, disp_ceiling=6.0)
     g.integrate_depth(d, R[None], T[None])
     o.integrate_depth(R, T, d)
     ng, xg, cg = g.surface()
@@ -236,7 +245,10 @@ def test_full_size_properties_512():
     g.integrate_depth(d, Rs, Ts)
     i2, t2, w2, _ = as_dict_rows(*g.gather())
     assert np.array_equal(i1, i2)
-    assert np.allclose(w2, 2.0 * w1, rtol=1e-5)
+    free = w2 < 999.0  # Wmax clamp (dense_tsdf.py:267) binds next to the camera, where thousands of rays overlap
+    assert free.mean() > 0.9 and (~free).sum() > 0
+    assert np.allclose(w2[free], 2.0 * w1[free], rtol=1e-5)
+    assert np.all(w2[~free] == 1000.0)
     assert np.abs(t2 - t1).max() <= TOL
     assert g.stats()["n_updates"] == 2 * st1["n_updates"]
     g.reset()

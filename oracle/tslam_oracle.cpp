@@ -110,6 +110,15 @@ struct Pose {
   Pose() : R{1, 0, 0, 0, 1, 0, 0, 0, 1}, T{0, 0, 0} {}
 };
 
+// rows of the submap pose tables start at ZERO (ti fields, mapping_common.py:104-105)
+static inline Pose pose_or_zero(const std::unordered_map<int, Pose>& t, int s) {
+  auto it = t.find(s);
+  if (it != t.end()) return it->second;
+  Pose p;
+  memset(p.R, 0, sizeof(p.R));
+  return p;
+}
+
 struct TsdfCfg {  // mirrors the C struct in tslam_oracle.h (ctypes side)
   double voxel_scale;
   int N, Nz;
@@ -528,8 +537,7 @@ void orc_tsdf_fuse(void* hdst, void* hsrc) {
   std::sort(keys.begin(), keys.end());
   for (auto& key : keys) {
     Block* sb = S->blocks[key];
-    Pose P = D->submap_pose.count(key.s) ? D->submap_pose[key.s] : Pose();
-    if (!D->submap_pose.count(key.s)) { memset(P.R, 0, sizeof(P.R)); }  // unset pose table rows are zero (ti field default)
+    Pose P = pose_or_zero(D->submap_pose, key.s);
     for (int o = 0; o < OB3; o++) {
       if (!(sb->obs[o] > 0)) continue;  // :292
       int i = key.x * OB + o / (OB * OB), j = key.y * OB + (o / OB) % OB, k = key.z * OB + o % OB;
@@ -567,7 +575,7 @@ int64_t orc_tsdf_surface(void* h, int submap, int64_t cap, float* xyz, float* rg
   std::vector<Key> keys;
   for (auto& kv : m->blocks) if (kv.first.s == submap) keys.push_back(kv.first);
   std::sort(keys.begin(), keys.end());
-  Pose P = m->submap_pose.count(submap) ? m->submap_pose[submap] : Pose();
+  Pose P = pose_or_zero(m->submap_pose, submap);
   int64_t n = 0;
   for (auto& key : keys) {
     Block* b = m->blocks[key];
@@ -600,7 +608,7 @@ int64_t orc_tsdf_slice(void* h, int submap, float z, float dz, int64_t cap, floa
   std::vector<Key> keys;
   for (auto& kv : m->blocks) if (kv.first.s == submap) keys.push_back(kv.first);
   std::sort(keys.begin(), keys.end());
-  Pose P = m->submap_pose.count(submap) ? m->submap_pose[submap] : Pose();
+  Pose P = pose_or_zero(m->submap_pose, submap);
   int64_t n = 0;
   for (auto& key : keys) {
     Block* b = m->blocks[key];
@@ -884,7 +892,7 @@ int64_t orc_octo_export(void* h, int submap, int level, int64_t cap, float* xyz)
     Key c{submap, fdiv(kv.first.x + h2, g) * g - h2, fdiv(kv.first.y + h2, g) * g - h2, fdiv(kv.first.z + hz, g) * g - hz};
     cells[c] = 1;
   }
-  Pose P = m->submap_pose.count(submap) ? m->submap_pose[submap] : Pose();
+  Pose P = pose_or_zero(m->submap_pose, submap);
   int64_t n = 0;
   for (auto& kv : cells) {
     auto it = m->cnt.find(kv.first);
@@ -910,8 +918,7 @@ void orc_octo_fuse(void* hdst, void* hsrc) {
   for (auto& kv : S->cnt) {
     float occ = (float)kv.second;
     if (!(occ > (float)D->min_occupy_thres)) continue;  // :181
-    Pose P;
-    if (D->submap_pose.count(kv.first.s)) P = D->submap_pose[kv.first.s]; else memset(P.R, 0, sizeof(P.R));
+    Pose P = pose_or_zero(D->submap_pose, kv.first.s);
     float l[3] = {(float)kv.first.x * vs, (float)kv.first.y * vs, (float)kv.first.z * vs};
     float r[3];
     rot(P.R, l, r);

@@ -129,6 +129,7 @@ def test_submap_mapping_flow():
         bR, bT = bases[sid]
         so.integrate_depth((bR.T @ R).astype(np.float32), (bR.T @ (T - bT)).astype(np.float32), d, submap=sid)
     assert sm.submap_collection.get_active_submap_id() == 2 and len(sent) == 2
+    sm.submap_collection.finalization_current_submap()  # flushes the frame queue (frame 6 is still queued)
     for s in range(3):
         compare_voxels(sm.submap_collection._h.gather(s), so.gather(s), 1e-4)
     # wire format round trip of the first exported submap (zlib level-1 of np.save(dict), submap_mapping.py:226-233)
@@ -155,12 +156,15 @@ def test_octomap_class_surface():
     m = Octomap(map_scale=[51.2, 51.2], voxel_scale=0.05, K=2, min_occupy_thres=2, max_disp_particles=1 << 20)
     o = OracleOctomap(map_scale=[51.2, 51.2], voxel_scale=0.05, K=2, min_occupy_thres=2)
     assert (m.Rxy, m.N) == (10, 1024)
+    bR, bT = rot_xyz(0.0, 0.0, 0.5), np.array([0.2, 0.1, 0.0])
+    m.set_base_pose_submap(0, bR, bT)   # pose-table rows start at zero (mapping_common.py:106-107)
+    o.set_submap_pose(0, bR, bT)
     rng = np.random.default_rng(11)
     pts = (rng.normal(size=(60000, 3)) * 0.25 + np.array([0.5, 1.0, 0.2]))
     R, T = rot_xyz(0.1, 0.2, 0.3), np.array([0.3, 0.2, 0.1])
     for _ in range(4):
         m.recast_pcl_to_map(R, T, pts, np.array([]), pts.shape[0])  # f64 cloud like ros_numpy's; computed in f32
-        o.integrate_points(R.astype(np.float32), T.astype(np.float32), pts.astype(np.float32))
+        o.integrate_points((bR.T @ R).astype(np.float32), (bR.T @ (T - bT)).astype(np.float32), pts.astype(np.float32))
     gi, gc = as_dict_rows(*m.occupy)
     oi, oc = as_dict_rows(*o.gather())
     assert np.array_equal(gi, oi) and np.array_equal(gc, oc)

@@ -106,6 +106,9 @@ def test_octomap_c3_counts_bit_exact():
     g = OctoHandle(o.N, o.Nz, K=2, voxel_scale=0.05, min_occupy_thres=2)
     pts = syn.octo_cloud(100000, seed=1)
     R = rot_xyz(0.0, 0.0, 0.0)
+    Rs, Ts_ = rot_xyz(0.05, 0.1, -0.2), np.array([0.4, -0.3, 0.2])   # pose-table row of submap 0 (rows start at zero)
+    g.set_submap_pose(0, Rs, Ts_)
+    o.set_submap_pose(0, Rs, Ts_)
     g.integrate_points(pts, R, np.zeros(3))
     o.integrate_points(R, np.zeros(3), pts)
     gi, gc = as_dict_rows(*g.gather())

@@ -173,6 +173,7 @@ struct TsIntrin {
   float fx, fy, cx, cy;
   float dmin_mm, dmax_mm;  // f32(min_ray*1000), f32(max_ray*1000)
   float vs;
+  float rvs;               // RN(1/vs), for the exact FMA division in the march loop
   float max_steps;         // f32(max_ray_length / voxel_scale)
   float max_ray;           // f32(max_ray_length)
   int internal_voxels;

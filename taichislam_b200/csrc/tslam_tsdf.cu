@@ -48,6 +48,15 @@ extern "C" int tslam_device_count(void) {
 __device__ __forceinline__ int iroundf(float x) { return (int)roundf(x); }  // ti.round(x, i32) mapping_common.py:263-266
 __device__ __forceinline__ float sgnf(float v) { return (float)((0.0f < v) - (v < 0.0f)); }  // mapping_common.py:5-7
 
+// x / vs, correctly rounded, without the slow-path check of the generic IEEE division: rvs = RN(1/vs) comes
+// from the host; q1 = fma(fma(-q0, vs, x), rvs, q0) is the correctly rounded quotient (Markstein) for the
+// operand ranges that occur here (|x| < 1e4 m, vs ~ 1e-2..1 m: no overflow / underflow / denormals).
+__device__ __forceinline__ float div_vs(float x, float vs, float rvs) {
+  const float q0 = __fmul_rn(x, rvs);
+  const float e = __fmaf_rn(-q0, vs, x);
+  return __fmaf_rn(e, rvs, q0);
+}
+
 __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz) {
   return ((((unsigned long long)(bx + (1 << 20)) << 42) | ((unsigned long long)(by + (1 << 20)) << 21) |
            (unsigned long long)(bz + (1 << 20))) + 1ull);
@@ -203,7 +212,22 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
 #define RM_WIN 16
 #define RM_WIN3 4096
 #define RM_FIX 16777216.0f   // 2^24
-#define RM_SMEM (RM_WIN3 * 16)
+#define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
+#define RM_SMEM (RM_WIN3 * 16 + RM_TAB * 8)
+
+// block lookup for the march loop: shared-memory table first (global loads queue behind the reduction traffic in
+// the in-order L1TEX pipe: measured as the top stall), hash grid on a miss.
+__device__ __forceinline__ int rm_lookup(const TsGrid& g, unsigned long long* tab, unsigned long long key, int bx, int by, int bz) {
+  const int h = ((bx & 15) << 8) | ((by & 15) << 4) | (bz & 15);
+  const unsigned long long w = tab[h];
+  if ((w >> 24) == key) return (int)(w & TS_IDX_MASK);
+  const int blk = ts_get_or_alloc_cached(g, key);
+  if (blk >= 0) {
+    ts_mark_dirty(g, blk);
+    tab[h] = (key << 24) | (unsigned long long)blk;  // benign race: any writer stores a valid word
+  }
+  return blk;
+}
 
 __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
   const unsigned int ux = (unsigned int)x;
@@ -220,6 +244,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   int* const w_ahi = (int*)(win + RM_WIN3);
   unsigned int* const w_blo = win + 2 * RM_WIN3;
   int* const w_bhi = (int*)(win + 3 * RM_WIN3);
+  unsigned long long* const btab = (unsigned long long*)(win + 4 * RM_WIN3);
   __shared__ int s_org[4];   // window origin (voxels) and submap
   __shared__ int s_blk[8];   // the <= 8 blocks the window overlaps
 
@@ -227,7 +252,9 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   const float vs = in.vs;
   const uint32_t lane = threadIdx.x & 31u;
   unsigned int my_updates = 0, my_oob = 0, my_rays = 0;
+  const float rvs = in.rvs;
   for (int e = threadIdx.x; e < 4 * RM_WIN3; e += RM_THREADS) win[e] = 0u;
+  for (int e = threadIdx.x; e < RM_TAB; e += RM_THREADS) btab[e] = TS_EMPTY;
 
   // control flow is kept WARP-UNIFORM (32 consecutive rays per warp, march to the longest ray, predicated lanes)
   for (uint32_t base = blockIdx.x * RM_THREADS; base < n_rays; base += gridDim.x * RM_THREADS) {
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
     for (int it = 0; it < nmax; ++it) {
       jf += 1.0f;  // :252
       const float x = (ux * jf) * vs + Tx, y = (uy * jf) * vs + Ty, z = (uz * jf) * vs + Tz;  // :253
-      const int xi = iroundf(x / vs), yi = iroundf(y / vs), zi = iroundf(z / vs);           // :254
+      const int xi = iroundf(div_vs(x, vs, rvs)), yi = iroundf(div_vs(y, vs, rvs)), zi = iroundf(div_vs(z, vs, rvs));  // :254
       const float vx = Px - x, vy = Py - y, vz = Pz - z;                                      // :258
       const float d = sqrtf((vx * vx + vy * vy) + vz * vz);                                  // :259
       const float ds = d * sgnf((vx * mx + vy * my) + vz * mz);                              // :260
@@ -316,8 +343,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       const unsigned long long key = ts_pack_key(s, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
       if (far && key != cur_key) {  // block boundary crossed: ~ every 10th step of a lane
         cur_key = key;
-        cur_blk = ts_get_or_alloc_cached(g, key);
-        if (cur_blk >= 0) ts_mark_dirty(g, cur_blk);
+        cur_blk = rm_lookup(g, btab, key, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
       }
       __syncwarp();
       if (far && cur_blk >= 0) {  // cur_blk < 0: pool exhausted (error flag raised)
@@ -456,6 +482,7 @@ static void ts_fill_intrin(tslam_tsdf* m) {
   m->in.dmin_mm = (float)(c.min_ray_length * 1000.0);
   m->in.dmax_mm = (float)(c.max_ray_length * 1000.0);
   m->in.vs = (float)c.voxel_scale;
+  m->in.rvs = 1.0f / m->in.vs;
   m->in.max_steps = (float)(c.max_ray_length / c.voxel_scale);
   m->in.max_ray = (float)c.max_ray_length;
   m->in.internal_voxels = c.internal_voxels;

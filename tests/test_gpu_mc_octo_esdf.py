@@ -91,11 +91,23 @@ def test_mc_after_integration_c2():
         o.integrate_depth(Rs[q], Ts[q], d[q])
     no, ov, on = o.marching_cubes(1, 0.25)
     ng, gv, gn = g.marching_cubes(1, 0.25)
-    # TSDF values differ by ~1e-7 between the two sides: a corner within that distance of 0 could change a
-    # cube's case.  Allow a tiny count difference, and compare geometry as point clouds.
+    # (a) end to end: TSDF values differ by ~1e-5 between the two sides; a vertex sits at mu = -v1/(v2-v1), so that
+    # difference is amplified by vs/|v2-v1| where the field is flat, and a corner within 1e-5 of zero can change a
+    # cube's case.  Counts agree to 1e-4, geometry to 2 mm (and to 1e-4 m for 99% of the vertices).
     assert abs(ng - no) <= max(4, int(1e-4 * no)) and no > 10000
     if ng == no:
-        mesh_equal(gv, gn, ov, on, tol=1e-4)
+        kg = np.lexsort(np.round(gv.reshape(-1, 9), 2).T[::-1])
+        ko = np.lexsort(np.round(ov.reshape(-1, 9), 2).T[::-1])
+        dv = np.abs(gv.reshape(-1, 9)[kg] - ov.reshape(-1, 9)[ko]).max(1)
+        assert np.quantile(dv, 0.99) <= 1e-4 and dv.max() <= 2e-3
+    # (b) the mesher itself: on IDENTICAL TSDF values (the GPU's map loaded into a fresh oracle) the two
+    # meshes agree to 1e-6 in every vertex and normal.
+    gi, gt, gw, gocc = g.gather()
+    o2 = OracleTSDF(map_scale=[25.6, 25.6], K=syn.K_DEPTH, is_global_map=True)
+    o2.scatter(0, gi, gt, gw, gocc)
+    n2, v2, nr2 = o2.marching_cubes(1, 0.25)
+    assert n2 == ng
+    mesh_equal(gv, gn, v2, nr2, tol=1e-6)
 
 
 def test_octomap_c3_counts_bit_exact():

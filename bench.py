@@ -37,6 +37,22 @@ POOL_BATCHES = 4        # distinct input batches cycled through: 4*64*614 KB = 1
 MAP_SCALE = [25.6, 25.6]  # 512^3 voxels of 0.05 m (C2)
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this same command (profiles/)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for fn in sorted(os.listdir(pdir)):
+            if fn.endswith("_traffic.json"):
+                try:
+                    d = json.load(open(os.path.join(pdir, fn)))
+                    if kernel in d:
+                        best = (float(d[kernel]), fn)
+                except Exception:
+                    pass
+    return best
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -315,7 +331,9 @@ def main():
                    "frames_per_step": BATCH, "grid": "512^3", "parallelism": f"submap-sharded x{world} (no data-path collective)",
                    "l2": f"inputs cycle through {POOL_BATCHES} batches = {POOL_BATCHES * BATCH * syn.H * syn.W * 2 / 1e6:.0f} MB > 126 MB L2"},
         "roofline": {"bound": "hbm", "kernel": "k_raymarch", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": (load_traffic("k_raymarch") or (None, None))[0], "traffic_source": (load_traffic("k_raymarch") or (None, None))[1],
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": {"bucket": bucket_ms, "raymarch": ray_ms, "commit": commit_ms},
                      "algorithmic_bytes_per_frame_all_kernels": frame_bytes},
         "clocks": clocks,

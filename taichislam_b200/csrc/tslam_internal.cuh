@@ -220,6 +220,14 @@ struct tslam_tsdf {
   long long prof_launches;  // integrate launches recorded since profiling was switched on
   int sm_count;
   bool clamp_on_commit;
+  // frame queue of the per-frame API (tslam_tsdf_queue_depth): double-buffered device staging fed by a copy stream
+  int q_n, q_buf, q_h, q_w;
+  float q_R[TSLAM_MAX_BATCH * 9];
+  float q_T[TSLAM_MAX_BATCH * 3];
+  int q_s[TSLAM_MAX_BATCH];
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied[2], ev_free[2];
+  bool ev_free_valid[2];
 };
 
 // ---------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <cuda_fp16.h>
@@ -79,12 +80,12 @@ __device__ __forceinline__ void red_add_u32(unsigned int* addr, unsigned int v) 
 // process_point (dense_tsdf.py:227-234) with exact fixed-point sums.  Lanes of a warp that fall into
 // the same bucket (neighbouring pixels usually do) are merged first (match.any + redux): one probe and
 // one set of reductions per distinct bucket per warp instead of per pixel.  Must be called by all 32
-// lanes; `valid` masks lanes without a point.
-__device__ __forceinline__ void bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, uint32_t tab_base, float px, float py,
-                                                  float pz, float dep, float vs, bool agg_ok, uint32_t* ray_list, int* n_rays,
-                                                  uint32_t ray_cap, int* err) {
+// lanes; `valid` masks lanes without a point.  Returns the table slot when this lane OPENED a bucket
+// (the bucket becomes one ray; the caller appends it to the ray list), else -1.
+__device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, float px, float py, float pz, float dep,
+                                                 float vs, bool agg_ok, int* err) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return;
+  if (!valid) return -1;
   const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
   const unsigned long long key = bucket_key(bx, by, bz);
   long long qx = __float2ll_rn(px * FIXQ), qy = __float2ll_rn(py * FIXQ), qz = __float2ll_rn(pz * FIXQ), qd = __float2ll_rn(dep * FIXQ);
@@ -99,18 +100,18 @@ __device__ __forceinline__ void bucket_accumulate(bool valid, TsBucket* tab, uin
       qz = (long long)__reduce_add_sync(grp, (int)qz);
       qd = (long long)__reduce_add_sync(grp, (int)qd);
     }
-    if (!leader) return;
+    if (!leader) return -1;
   }
   uint32_t h = ts_hash(key) & cap_mask;
   TsBucket* b = nullptr;
+  int fresh = -1;
   for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
     TsBucket* c = &tab[h];
     unsigned long long cur = ts_ld_volatile(&c->key);
     if (cur == 0ull) {
       const unsigned long long prev = atomicCAS(&c->key, 0ull, key);
       if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
-        const uint32_t p = (uint32_t)atomicAdd(n_rays, 1);
-        if (p < ray_cap) ray_list[p] = tab_base + h; else atomicOr(err, TS_ERR_RAYLIST_FULL);
+        fresh = (int)h;
         b = c;
         break;
       }
@@ -119,12 +120,36 @@ __device__ __forceinline__ void bucket_accumulate(bool valid, TsBucket* tab, uin
     if (cur == key) { b = c; break; }
     h = (h + 1) & cap_mask;
   }
-  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return; }
+  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return -1; }
   red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
   red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
   red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
   red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
   red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
+  return fresh;
+}
+
+// CTA-aggregated append of the buckets opened by this CTA (one atomic on the global ray counter per CTA instead
+// of one per ray; the rays of a pixel tile stay contiguous in the list).  Must be reached by all threads.
+__device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_base, unsigned n_valid_warp, uint32_t* ray_list,
+                                                int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
+  __shared__ unsigned int s_cnt[8], s_val[8];
+  __shared__ unsigned int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, fresh_slot >= 0);
+  if (lane == 0) { s_cnt[wid] = __popc(m); s_val[wid] = n_valid_warp; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0, nv = 0;
+    for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; nv += s_val[w]; }
+    s_base = tot ? (unsigned)atomicAdd(n_rays, (int)tot) : 0u;
+    if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
+  }
+  __syncthreads();
+  if (fresh_slot >= 0) {
+    const uint32_t p = s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1));
+    if (p < ray_cap) ray_list[p] = tab_base + (uint32_t)fresh_slot; else atomicOr(err, TS_ERR_RAYLIST_FULL);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -160,12 +185,9 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, (uint32_t)f * bucket_cap, px, py, pz, dep, in.vs,
-                    agg_ok != 0, ray_list, n_rays, ray_cap, err);
-  if (lane == 0) {
-    if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
-  }
+  const int fresh = bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err);
+  append_rays_cta(fresh, (uint32_t)f * bucket_cap, nv, ray_list, n_rays, ray_cap, ctr, err);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
 }
 
 // K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
@@ -186,8 +208,8 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
     valid = len < in.max_ray;                          // :177
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  bucket_accumulate(valid, buckets, bucket_cap - 1, 0u, px, py, pz, len, in.vs, agg_ok != 0, ray_list, n_rays, ray_cap, err);  // :185
-  if ((threadIdx.x & 31) == 0 && nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
+  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err);  // :185
+  append_rays_cta(fresh, 0u, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
 
@@ -423,6 +445,96 @@ __global__ void __launch_bounds__(256) k_commit(TsGrid g, int clamp, int fused_o
     if (threadIdx.x == 0) g.dirty_flag[blk] = 0;
   }
 }
+// ---------------------------------------------------------------------------
+// K3 (TMA variant): the same commit, with each dirty block's two 32 KB planes moved by the bulk-copy engine
+// (cp.async.bulk: SASS UBLKCP) instead of per-thread loads/stores: one elected thread arms an mbarrier with the
+// expected byte count and issues two global->shared bulk copies; the CTA waits on the barrier, folds the sums in
+// shared memory, and the elected thread streams the updated (TSDF, W) plane and a zeroed accumulator plane back
+// with shared->global bulk stores.
+// ---------------------------------------------------------------------------
+#define CM_PLANE_BYTES (TS_B3 * 8)
+#define CM_SMEM (2 * CM_PLANE_BYTES + 16)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_commit_tma(TsGrid g, int clamp, int fused_obs) {
+  extern __shared__ __align__(128) unsigned char cm_smem[];
+  float2* s_acc = reinterpret_cast<float2*>(cm_smem);
+  float2* s_tw = reinterpret_cast<float2*>(cm_smem + CM_PLANE_BYTES);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(cm_smem + 2 * CM_PLANE_BYTES);
+  const int nd = *g.n_dirty;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase = 0;
+  for (int q = blockIdx.x; q < nd; q += gridDim.x) {
+    const int blk = g.dirty_list[q];
+    float2* acc = g.acc + (size_t)blk * TS_B3;
+    float2* tw = g.tw + (size_t)blk * TS_B3;
+    uint8_t* obs = g.obs + (size_t)blk * TS_B3;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, 2 * CM_PLANE_BYTES);
+      bulk_g2s(s_acc, acc, CM_PLANE_BYTES, bar);
+      bulk_g2s(s_tw, tw, CM_PLANE_BYTES, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
+      const float2 a = s_acc[v];
+      const bool touched = fused_obs ? (a.y != 0.0f || a.x != 0.0f || obs[v] == 2) : (a.y > 0.0f);
+      if (touched) {
+        const float2 o = s_tw[v];
+        const float wn = o.y + a.y;
+        float2 r;
+        r.x = (o.x * o.y + a.x) / wn;
+        r.y = clamp ? fminf(wn, WMAX) : wn;
+        s_tw[v] = r;
+        obs[v] = 1;
+        s_acc[v] = make_float2(0.0f, 0.0f);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the bulk engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(tw, s_tw, CM_PLANE_BYTES);
+      bulk_s2g(acc, s_acc, CM_PLANE_BYTES);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be overwritten by the next block's loads
+      g.dirty_flag[blk] = 0;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // compact the per-block dirty flags into dirty_list (warp-aggregated append)
 __global__ void __launch_bounds__(256) k_collect_dirty(TsGrid g) {
   const int nb = min(*g.n_blocks, g.max_blocks);
@@ -565,7 +677,12 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   m->ray_list_cap = (uint32_t)((size_t)TSLAM_MAX_BATCH * sampled);
   if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
   TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
-  TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));
+  TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)2 * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));  // double buffered
+  TS_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    TS_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+    TS_CUDA(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
+  }
   TS_CUDA(cudaMalloc(&m->points_stage, (size_t)m->cfg.max_points * 12));
   TS_CUDA(cudaMalloc(&m->counters, sizeof(TsCounters)));
   TS_CUDA(cudaMemset(m->counters, 0, sizeof(TsCounters)));
@@ -578,6 +695,7 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   TS_CUDA(cudaMalloc(&m->colormap, cm.size() * 4));
   TS_CUDA(cudaMemcpy(m->colormap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice));
   TS_CUDA(cudaFuncSetAttribute(k_raymarch, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_commit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM));
   TS_CUDA(cudaDeviceSynchronize());
   *out = m;
   return TSLAM_OK;
@@ -591,6 +709,8 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (g.esdf) cudaFree(g.esdf);
   cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
+  cudaStreamDestroy(m->copy_stream);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
   cudaFree(m->counters); cudaFree(m->pose_R); cudaFree(m->pose_T); cudaFree(m->colormap);
   if (m->ev) { for (int i = 0; i < 4 * TS_PROF_RING; i++) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
   delete m;
@@ -603,6 +723,7 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
   TsGrid& g = m->g;
   int nb = 0;
   m->n_integrate_calls = 0;  // pending sums are discarded with the blocks
+  m->q_n = 0;                // ... and so are queued frames
   TS_CUDA(cudaMemcpyAsync(&nb, g.n_blocks, 4, cudaMemcpyDeviceToHost, st));
   TS_CUDA(cudaStreamSynchronize(st));
   if (nb > g.max_blocks) nb = g.max_blocks;
@@ -641,14 +762,21 @@ static int ts_launch_commit(tslam_tsdf* m, cudaStream_t st, int clamp, int fused
   int grid = m->sm_count * 8;
   k_collect_dirty<<<(m->g.max_blocks + 255) / 256 < m->sm_count * 4 ? (m->g.max_blocks + 255) / 256 : m->sm_count * 4, 256, 0, st>>>(m->g);
   TS_LAUNCH_CHECK(m);
-  k_commit<<<grid, 256, 0, st>>>(m->g, clamp, fused);
+  static const bool plain = getenv("TSLAM_COMMIT_PLAIN") != nullptr;  // A/B switch for the non-TMA variant
+  if (plain) k_commit<<<grid, 256, 0, st>>>(m->g, clamp, fused);
+  else k_commit_tma<<<m->sm_count * 3, 256, CM_SMEM, st>>>(m->g, clamp, fused);
   TS_LAUNCH_CHECK(m);
   k_reset_counters<<<1, 1, 0, st>>>(m->g.n_dirty, nullptr);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }
 
+static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st);
 int ts_flush_pending(tslam_tsdf* m, cudaStream_t st) {
+  if (m->q_n > 0) {  // frames queued by the per-frame API
+    int rc = ts_launch_queue(m, st);
+    if (rc) return rc;
+  }
   if (m->n_integrate_calls > 0) {  // something may be pending
     int rc = ts_launch_commit(m, st, m->clamp_on_commit ? 1 : 0, 0);
     if (rc) return rc;
@@ -763,6 +891,58 @@ extern "C" int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, in
     if (rc) return rc;
   }
   if (pe) { TS_CUDA(cudaEventRecord(pe[3], st)); m->prof_launches++; }
+  return TSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-frame queue: the reference API hands over ONE frame per call (recast_depth_to_map, dense_tsdf.py:162-165).
+// tslam_tsdf_queue_depth copies the frame to a device staging slot on a copy stream (overlapping the kernels of
+// the previous batch) and records its pose; a full queue (TSLAM_MAX_BATCH frames) or tslam_tsdf_flush launches
+// the batch: bucket -> ray march -> commit.
+// ---------------------------------------------------------------------------
+static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
+  const int n = m->q_n;
+  if (n == 0) return TSLAM_OK;
+  const int b = m->q_buf;
+  TS_CUDA(cudaEventRecord(m->ev_copied[b], m->copy_stream));
+  TS_CUDA(cudaStreamWaitEvent(st, m->ev_copied[b], 0));
+  const uint16_t* src = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels;
+  m->q_n = 0;  // (integrate may recurse into flush through readers; the queue is empty from here on)
+  m->q_buf = b ^ 1;
+  int rc = tslam_tsdf_integrate_depth(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st);
+  if (rc) return rc;
+  TS_CUDA(cudaEventRecord(m->ev_free[b], st));
+  m->ev_free_valid[b] = true;
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  return ts_launch_queue(m, (cudaStream_t)stream);
+}
+
+extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
+                                      const float* T3, int32_t submap, void* stream) {
+  if (!m || !depth_host || !R9 || !T3 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
+  if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->q_n > 0 && (m->q_h != h || m->q_w != w)) {
+    int rc = ts_launch_queue(m, st);
+    if (rc) return rc;
+  }
+  const int b = m->q_buf, q = m->q_n;
+  if (q == 0) {
+    m->q_h = h; m->q_w = w;
+    if (m->ev_free_valid[b]) TS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_free[b], 0));  // kernels that read this buffer are done
+  }
+  uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
+  TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  memcpy(m->q_R + 9 * q, R9, 36);
+  memcpy(m->q_T + 3 * q, T3, 12);
+  m->q_s[q] = submap;
+  m->q_n = q + 1;
+  if (m->q_n == TSLAM_MAX_BATCH) return ts_launch_queue(m, st);
   return TSLAM_OK;
 }
 

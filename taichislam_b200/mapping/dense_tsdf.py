@@ -62,16 +62,6 @@ class DenseTSDF(BaseMap):
                              max_image_pixels=max_image_pixels)
         self.initialize_submap_fields(self.max_submap_num)
         self._init_export_fields()
-        # frame queue (pinned, double buffered)
-        self._qcap = capi.MAX_BATCH
-        self._stage = None
-        self._stage_shape = None
-        self._q_n = 0
-        self._q_buf = 0
-        self._q_R = np.zeros((self._qcap, 9), np.float32)
-        self._q_T = np.zeros((self._qcap, 3), np.float32)
-        self._q_s = np.zeros(self._qcap, np.int32)
-        self._stage_ev = [None, None]
         print(f"TSDF map initialized blocks {self.block_num_xy}x{self.block_num_xy}x{self.block_num_z}")
 
     # ------------------------------------------------------------------ fields (dense_tsdf.py:52-60, :129-134)
@@ -96,52 +86,26 @@ class DenseTSDF(BaseMap):
         self._h.set_submap_pose(submap_id, R, T)
 
     # ------------------------------------------------------------------ integrate (dense_tsdf.py:157-165)
-    def _ensure_stage(self, h, w):
-        torch = self._torch
-        if self._stage_shape != (h, w):
-            self._flush()
-            self._stage = [torch.empty((self._qcap, h, w), dtype=torch.int16).pin_memory() for _ in range(2)]
-            self._stage_np = [s.numpy().view(np.uint16) for s in self._stage]
-            self._stage_shape = (h, w)
-
     def recast_depth_to_map(self, R, T, depthmap, texture):
-        """Queue one depth frame (uint16 mm [h,w]); integrated with the next batch (:162-165)."""
+        """Queue one depth frame (uint16 mm [h,w]); the library integrates queued frames in batches (:162-165).
+        The frame is copied to the device right away (asynchronously when `depthmap` is pinned host memory)."""
         if self.K_cam_dep is None:
             raise RuntimeError("set_dep_camera_intrinsic() must be called before recast_depth_to_map")
         self.set_pose(R, T)
-        depthmap = np.asarray(depthmap)
+        if depthmap.dtype != np.uint16 or not depthmap.flags.c_contiguous:
+            depthmap = np.ascontiguousarray(depthmap, dtype=np.uint16)
         h, w = depthmap.shape
-        self._ensure_stage(h, w)
-        if self._q_n == 0 and self._stage_ev[self._q_buf] is not None:
-            self._stage_ev[self._q_buf].synchronize()  # the previous H2D copy out of this buffer has finished
-        q = self._q_n
-        self._stage_np[self._q_buf][q] = depthmap
-        self._q_R[q] = self.input_R_np.reshape(9)
-        self._q_T[q] = self.input_T_np
-        self._q_s[q] = 0 if self.is_global_map else self.active_submap_id[None]
-        self._q_n = q + 1
-        if self._q_n == self._qcap:
-            self._launch_queue()
+        sid = 0 if self.is_global_map else self.active_submap_id.v
+        rc = self._h.L.tslam_tsdf_queue_depth(self._h.h, depthmap.ctypes.data, h, w, self.input_R_np.ctypes.data,
+                                              self.input_T_np.ctypes.data, sid, self._stream_ptr())
+        if rc:
+            capi.check(rc)
 
-    def _launch_queue(self):
-        n = self._q_n
-        if n == 0:
-            return
-        torch = self._torch
-        L = self._h.L
-        st = self._stage[self._q_buf]
-        capi.check(L.tslam_tsdf_integrate_depth(self._h.h, capi.C.c_void_p(st.data_ptr()), capi.MEM_HOST, n,
-                                                self._stage_shape[0], self._stage_shape[1], capi.np_ptr(self._q_R),
-                                                capi.np_ptr(self._q_T), capi.np_ptr(self._q_s), capi.F_COMMIT,
-                                                capi.stream_ptr()))
-        ev = torch.cuda.Event()
-        ev.record()
-        self._stage_ev[self._q_buf] = ev
-        self._q_buf ^= 1
-        self._q_n = 0
+    def _stream_ptr(self):
+        return self._torch.cuda.current_stream().cuda_stream
 
     def _flush(self):
-        self._launch_queue()
+        capi.check(self._h.L.tslam_tsdf_flush(self._h.h, self._stream_ptr()))
 
     def recast_pcl_to_map(self, R, T, xyz_array, rgb_array):
         """:157-160.  xyz_array [n,3] (any float dtype; computed in f32 like the kernel's ti.f32 cast, :171-174)."""
@@ -154,13 +118,11 @@ class DenseTSDF(BaseMap):
 
     # ------------------------------------------------------------------ submaps / fusion (:272-318)
     def reset(self):
-        self._q_n = 0
         self._h.reset()
 
     def fuse_submaps(self, submaps):
         submaps._flush()
         t = time.time()
-        self._q_n = 0
         self._h.fuse_from(submaps._h)
         print(f"[DenseTSDF] Fuse submaps {(time.time() - t) * 1000:.1f}ms, active local: {submaps.active_submap_id[None]} "
               f"remote: {submaps.remote_submap_num[None]}")

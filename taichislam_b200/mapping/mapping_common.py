@@ -87,5 +87,5 @@ class BaseMap:
 
     def set_pose(self, _R, _T):  # :149-156
         _R, _T = self.convert_by_base(_R, _T)
-        self.input_R_np = _R.astype(np.float32)
-        self.input_T_np = _T.astype(np.float32)
+        self.input_R_np = np.ascontiguousarray(_R, dtype=np.float32)
+        self.input_T_np = np.ascontiguousarray(_T, dtype=np.float32)

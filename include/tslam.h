@@ -146,6 +146,34 @@ int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on);
 int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out);
 
 /* ----------------------------------------------------------------------------
+ * Multi-GPU: spatially tiled global map (one process per GPU).  The global volume is cut into
+ * tiles3[0] x tiles3[1] x tiles3[2] == world tiles of whole 16^3 blocks, tile t owned by rank t.  The library
+ * packs / unpacks voxel blocks into caller DEVICE buffers; the caller exchanges them (NCCL all-to-all).
+ * Keys are the library's packed block keys (opaque int64).  Planes per block: 4096 voxels.
+ * --------------------------------------------------------------------------*/
+/* fuse_submaps_kernel (dense_tsdf.py:282-307) of this rank's submaps, sums left PENDING (no commit). */
+int tslam_tsdf_fuse_pending(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* stream);
+/* Fold pending fusion sums (no Wmax clamp, dense_tsdf.py:274-278). */
+int tslam_tsdf_commit_fused(tslam_tsdf_t* m, void* stream);
+/* Owner rank of block (bx,by,bz). */
+int tslam_tiling_owner(tslam_tsdf_t* m, const int32_t* tiles3, int32_t world, int32_t bx, int32_t by, int32_t bz, int32_t* owner);
+/* counts_out[world] (HOST): touched blocks owned by every other rank.  Synchronises. */
+int tslam_tsdf_foreign_count(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, int32_t* counts_out, void* stream);
+/* Pack those blocks grouped by destination rank and clear them locally: keys int64[cap], acc f32[cap,4096,2]
+ * (pending sums), obs u8[cap,4096], occ i8[cap,4096].  Synchronises. */
+int tslam_tsdf_foreign_pack(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
+                            int64_t cap, int64_t* keys, float* acc, uint8_t* obs, int8_t* occ, void* stream);
+/* Add received blocks into the local map (sums stay pending until tslam_tsdf_commit_fused). */
+int tslam_tsdf_unpack_add(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* acc, const uint8_t* obs, const int8_t* occ,
+                          void* stream);
+/* Halo for meshing: blocks of the one-block boundary layer of this rank's tile, once per neighbouring tile. */
+int tslam_tsdf_halo_count(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, int32_t* counts_out, void* stream);
+int tslam_tsdf_halo_pack(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts, int64_t cap,
+                         int64_t* keys, float* tw, uint8_t* obs, void* stream);
+/* Insert received halo blocks as GHOSTS: read by marching cubes, never counted / exported / meshed as owners. */
+int tslam_tsdf_ghost_unpack(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* tw, const uint8_t* obs, void* stream);
+
+/* ----------------------------------------------------------------------------
  * Marching cubes  (MarchingCubeMesher, marching_cube_mesher.py)
  * --------------------------------------------------------------------------*/
 /* generate_mesh_kernel (marching_cube_mesher.py:127-187): two-pass (count, scan,

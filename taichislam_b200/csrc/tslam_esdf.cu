@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_esdf_gather(TsGrid g, int submap, long 
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;
+    if (s != submap || g.ghost[b]) continue;
     const size_t base = (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       const bool want = g.obs[base + v] > 0;

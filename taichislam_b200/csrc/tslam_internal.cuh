@@ -44,6 +44,7 @@ struct TsGrid {
   float2* tw;                 // [max_blocks*4096]
   uint8_t* obs;               // [max_blocks*4096]
   int8_t* occ;                // [max_blocks*4096]
+  uint8_t* ghost;             // [max_blocks] 1 = halo copy of a block owned by another rank (multi-GPU tiling)
   float* esdf;                // [max_blocks*4096] (allocated lazily by the ESDF path)
   int* dirty_flag;            // [max_blocks]
   int* dirty_list;            // [max_blocks]

@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(256) k_mc_count(TsGrid g, float thres, unsigne
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (g.ghost[b]) {  // halo copy: its cells belong to the owning rank
+      if (threadIdx.x == 0) blk_tris[b] = 0;
+      continue;
+    }
     __syncthreads();
     mc_stage(g, tile, s, bx, by, bz);
     unsigned int n = 0;
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float th
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (g.ghost[b]) continue;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       const int i = bx * TS_B + (v >> 8), j = by * TS_B + ((v >> 4) & 15), k = bz * TS_B + (v & 15);
       const size_t off = (size_t)b * TS_B3 + v;

@@ -653,6 +653,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   TS_CUDA(cudaMemset(g.obs, 0, nv));
   TS_CUDA(cudaMemset(g.occ, 0, nv));
   g.esdf = nullptr;
+  TS_CUDA(cudaMalloc(&g.ghost, (size_t)g.max_blocks));
+  TS_CUDA(cudaMemset(g.ghost, 0, (size_t)g.max_blocks));
   TS_CUDA(cudaMalloc(&g.dirty_flag, (size_t)g.max_blocks * 4));
   TS_CUDA(cudaMalloc(&g.dirty_list, (size_t)g.max_blocks * 4));
   TS_CUDA(cudaMemset(g.dirty_flag, 0, (size_t)g.max_blocks * 4));
@@ -707,7 +709,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   TsGrid& g = m->g;
   cudaFree(g.table); cudaFree(g.block_key); cudaFree(g.acc); cudaFree(g.tw); cudaFree(g.obs); cudaFree(g.occ);
   if (g.esdf) cudaFree(g.esdf);
-  cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
+  cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
@@ -736,6 +738,7 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
     TS_CUDA(cudaMemsetAsync(g.occ, 0, nv, st));
     if (g.esdf) TS_CUDA(cudaMemsetAsync(g.esdf, 0, nv * 4, st));
     TS_CUDA(cudaMemsetAsync(g.dirty_flag, 0, (size_t)nb * 4, st));
+    TS_CUDA(cudaMemsetAsync(g.ghost, 0, (size_t)nb, st));
   }
   TS_CUDA(cudaMemsetAsync(m->scratch_i, 0, 4 * sizeof(int), st));  // n_blocks, n_dirty, err, n_rays
   return TSLAM_OK;
@@ -955,7 +958,7 @@ __global__ void __launch_bounds__(256) k_count_active(TsGrid g, int submap, unsi
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;
+    if (s != submap || g.ghost[b]) continue;
     const uint8_t* obs = g.obs + (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) c += obs[v] > 0;
   }
@@ -991,7 +994,7 @@ __global__ void __launch_bounds__(256) k_gather(TsGrid g, int submap, long long 
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;
+    if (s != submap || g.ghost[b]) continue;
     const size_t base = (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       const bool want = g.obs[base + v] > 0;
@@ -1093,7 +1096,7 @@ __global__ void __launch_bounds__(256) k_extract_surface(TsGrid g, int submap, i
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;  // :348
+    if (s != submap || g.ghost[b]) continue;  // :348
     const size_t base = (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       bool want = false;
@@ -1124,7 +1127,7 @@ __global__ void __launch_bounds__(256) k_extract_slice(TsGrid g, int submap, int
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;  // :375
+    if (s != submap || g.ghost[b]) continue;  // :375
     const size_t base = (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       const int k = bz * TS_B + (v & 15);
@@ -1203,6 +1206,7 @@ __global__ void __launch_bounds__(256) k_fuse(TsGrid dst, TsGrid src, const floa
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(src.block_key[b], s, bx, by, bz);
+    if (src.ghost[b]) continue;
     const float* R = pR + 9 * s;
     const float* T = pT + 3 * s;
     const size_t base = (size_t)b * TS_B3;
@@ -1251,6 +1255,24 @@ extern "C" int tslam_tsdf_fuse(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* strea
   k_fuse<<<dst->sm_count * 8, 256, 0, st>>>(dst->g, src->g, dst->pose_R, dst->pose_T, dst->in.vs);
   TS_LAUNCH_CHECK(dst);
   return ts_launch_commit(dst, st, 0, 1);
+}
+
+// multi-GPU building blocks (see tslam_dist.cu): fusion that leaves its sums pending, and the fused commit
+extern "C" int tslam_tsdf_fuse_pending(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* stream) {
+  if (!dst || !src || dst == src) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts_flush_pending(src, st);
+  if (rc) return rc;
+  dst->n_integrate_calls = 0;
+  rc = tslam_tsdf_reset(dst, stream);
+  if (rc) return rc;
+  k_fuse<<<dst->sm_count * 8, 256, 0, st>>>(dst->g, src->g, dst->pose_R, dst->pose_T, dst->in.vs);
+  TS_LAUNCH_CHECK(dst);
+  return TSLAM_OK;
+}
+extern "C" int tslam_tsdf_commit_fused(tslam_tsdf_t* m, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  return ts_launch_commit(m, (cudaStream_t)stream, 0, 1);
 }
 
 // ---------------------------------------------------------------------------

@@ -373,27 +373,48 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
         my_updates++;
       }
     }
-    // flush the window: one reduction per touched voxel
+    // flush the window: one reduction per touched voxel.  Pass 1 finds which of the <= 8 overlapped blocks hold
+    // touched voxels, 8 threads resolve (activate) exactly those, pass 2 emits the reductions.
     __syncthreads();
-    if (threadIdx.x < 8) s_blk[threadIdx.x] = -2;  // the <= 8 overlapped blocks are resolved lazily below
+    if (threadIdx.x < 8) s_blk[threadIdx.x] = 0;
+    __syncthreads();
+    {
+      unsigned need = 0;
+      for (int e = threadIdx.x; e < RM_WIN3; e += RM_THREADS) {
+        if (w_blo[e] == 0u && w_bhi[e] == 0) continue;  // B > 0 for every sample (w > 0)
+        const int xi = wx + (e >> 8), yi = wy + ((e >> 4) & 15), zi = wz + (e & 15);
+        need |= 1u << ((((xi >> TS_BSHIFT) - (wx >> TS_BSHIFT)) << 2) | (((yi >> TS_BSHIFT) - (wy >> TS_BSHIFT)) << 1) |
+                       ((zi >> TS_BSHIFT) - (wz >> TS_BSHIFT)));
+      }
+      need = __reduce_or_sync(0xffffffffu, need);
+      if (lane == 0) {
+        for (int b8 = 0; b8 < 8; b8++)
+          if (need & (1u << b8)) atomicOr((unsigned int*)&s_blk[b8], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      int blk = -1;
+      if (s_blk[threadIdx.x]) {
+        blk = ts_get_or_alloc_cached(g, ts_pack_key(ws, (wx >> TS_BSHIFT) + ((threadIdx.x >> 2) & 1), (wy >> TS_BSHIFT) + ((threadIdx.x >> 1) & 1),
+                                                    (wz >> TS_BSHIFT) + (threadIdx.x & 1)));
+        if (blk >= 0) ts_mark_dirty(g, blk);
+      }
+      s_blk[threadIdx.x] = blk;
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < RM_WIN3; e += RM_THREADS) {
       const unsigned int blo = w_blo[e];
       const int bhi = w_bhi[e];
-      if (blo == 0u && bhi == 0) continue;  // B > 0 for every sample (w > 0)
+      if (blo == 0u && bhi == 0) continue;
       const unsigned int alo = w_alo[e];
       const int ahi = w_ahi[e];
       w_alo[e] = 0u; w_ahi[e] = 0; w_blo[e] = 0u; w_bhi[e] = 0;
       const int xi = wx + (e >> 8), yi = wy + ((e >> 4) & 15), zi = wz + (e & 15);
       const int bsel = (((xi >> TS_BSHIFT) - (wx >> TS_BSHIFT)) << 2) | (((yi >> TS_BSHIFT) - (wy >> TS_BSHIFT)) << 1) |
                        ((zi >> TS_BSHIFT) - (wz >> TS_BSHIFT));
-      int blk = *(volatile int*)&s_blk[bsel];
-      if (blk == -2) {
-        blk = ts_get_or_alloc_cached(g, ts_pack_key(ws, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT));
-        if (blk >= 0) ts_mark_dirty(g, blk);
-        *(volatile int*)&s_blk[bsel] = blk;  // benign race: every writer stores the same value
-      }
-      if (blk < 0) continue;
+      const int blk = s_blk[bsel];
+      if (blk < 0) continue;  // pool exhausted (error flag raised)
       const float A = (float)(((double)ahi * 4294967296.0 + (double)alo) * (1.0 / 16777216.0));
       const float B = (float)(((double)bhi * 4294967296.0 + (double)blo) * (1.0 / 16777216.0));
       red_add_f32x2(&g.acc[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], A, B);

@@ -146,6 +146,19 @@ int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on);
 int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out);
 
 /* ----------------------------------------------------------------------------
+ * Map queries for planners - batched forms of the @ti.func helpers of BaseMap (mapping_common.py:165-204) that
+ * TopoGraphGen calls from its kernels (topo_graph.py:444-507).  All arrays DEVICE, n entries.
+ * --------------------------------------------------------------------------*/
+/* flags[i]: bit0 = is_pos_occupy (TSDF < 1.8*vs, dense_tsdf.py:152-155 - unobserved space reads 0, i.e. occupied),
+ * bit1 = is_pos_unobserved (dense_tsdf.py:148-150). */
+int tslam_tsdf_query_points(tslam_tsdf_t* m, int32_t submap, int64_t n, const float* xyz, uint8_t* flags, void* stream);
+/* is_near_pos_occupy (mapping_common.py:193-204): any occupied cell in [-voxel, voxel)^3 around the point. */
+int tslam_tsdf_query_near_occupy(tslam_tsdf_t* m, int32_t submap, int64_t n, const float* xyz, int32_t voxel, uint8_t* out, void* stream);
+/* raycast (mapping_common.py:165-178): step voxel_scale along dir until an occupied cell; hit, last position, length. */
+int tslam_tsdf_raycast(tslam_tsdf_t* m, int32_t submap, int64_t n, const float* pos, const float* dir, float max_dist, uint8_t* hit,
+                       float* xyz_out, float* len_out, void* stream);
+
+/* ----------------------------------------------------------------------------
  * Multi-GPU: spatially tiled global map (one process per GPU).  The global volume is cut into
  * tiles3[0] x tiles3[1] x tiles3[2] == world tiles of whole 16^3 blocks, tile t owned by rank t.  The library
  * packs / unpacks voxel blocks into caller DEVICE buffers; the caller exchanges them (NCCL all-to-all).
@@ -230,6 +243,10 @@ int tslam_octo_extract(tslam_octo_t* m, int32_t submap, int32_t level, int64_t c
                        void* stream);
 /* fuse_submaps_kernel (taichi_octomap.py:171-189) after reset(). */
 int tslam_octo_fuse(tslam_octo_t* dst, tslam_octo_t* src, void* stream);
+/* Octomap.is_occupy (taichi_octomap.py:86-88: occupy > min_occupy_thres) for points, and BaseMap.raycast. */
+int tslam_octo_query_points(tslam_octo_t* m, int32_t submap, int64_t n, const float* xyz, uint8_t* flags, void* stream);
+int tslam_octo_raycast(tslam_octo_t* m, int32_t submap, int64_t n, const float* pos, const float* dir, float max_dist, uint8_t* hit,
+                       float* xyz_out, float* len_out, void* stream);
 int tslam_octo_sync(tslam_octo_t* m, void* stream);
 int64_t tslam_octo_launch_count(tslam_octo_t* m);
 

@@ -84,6 +84,11 @@ def lib():
         L.orc_octo_export.argtypes = [vp, i32, i32, i64, vp]
         L.orc_octo_export.restype = i64
         L.orc_octo_fuse.argtypes = [vp, vp]
+        L.orc_tsdf_query_points.argtypes = [vp, i32, i64, vp, vp]
+        L.orc_tsdf_query_near.argtypes = [vp, i32, i64, vp, i32, vp]
+        L.orc_tsdf_raycast.argtypes = [vp, i32, i64, vp, vp, C.c_float, vp, vp, vp]
+        L.orc_octo_query_points.argtypes = [vp, i32, i64, vp, vp]
+        L.orc_octo_raycast.argtypes = [vp, i32, i64, vp, vp, C.c_float, vp, vp, vp]
         L.orc_tsdf_integrate_stream_mt.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
         L.orc_tsdf_integrate_stream_mt.restype = i32
         _lib = L
@@ -192,6 +197,25 @@ class OracleTSDF:
         m = min(n, cap_tri)
         return n, v[:3 * m], nrm[:3 * m]
 
+    def query_points(self, xyz, submap=0):
+        xyz = _f32(xyz)
+        f = np.zeros(xyz.shape[0], np.uint8)
+        lib().orc_tsdf_query_points(self.h, submap, xyz.shape[0], _p(xyz), _p(f))
+        return (f & 1).astype(bool), (f & 2).astype(bool)
+
+    def query_near_occupy(self, xyz, voxel, submap=0):
+        xyz = _f32(xyz)
+        f = np.zeros(xyz.shape[0], np.uint8)
+        lib().orc_tsdf_query_near(self.h, submap, xyz.shape[0], _p(xyz), int(voxel), _p(f))
+        return f.astype(bool)
+
+    def raycast(self, pos, direction, max_dist, submap=0):
+        pos, direction = _f32(pos), _f32(direction)
+        n = pos.shape[0]
+        hit = np.zeros(n, np.uint8); xyz = np.zeros((n, 3), np.float32); ln = np.zeros(n, np.float32)
+        lib().orc_tsdf_raycast(self.h, submap, n, _p(pos), _p(direction), float(max_dist), _p(hit), _p(xyz), _p(ln))
+        return hit.astype(bool), xyz, ln
+
     def esdf_update(self, submap=0):
         return int(lib().orc_esdf_update(self.h, submap))
 
@@ -253,6 +277,19 @@ class OracleOctomap:
 
     def fuse_from(self, src):
         lib().orc_octo_fuse(self.h, src.h)
+
+    def query_points(self, xyz, submap=0):
+        xyz = _f32(xyz)
+        f = np.zeros(xyz.shape[0], np.uint8)
+        lib().orc_octo_query_points(self.h, submap, xyz.shape[0], _p(xyz), _p(f))
+        return f.astype(bool)
+
+    def raycast(self, pos, direction, max_dist, submap=0):
+        pos, direction = _f32(pos), _f32(direction)
+        n = pos.shape[0]
+        hit = np.zeros(n, np.uint8); xyz = np.zeros((n, 3), np.float32); ln = np.zeros(n, np.float32)
+        lib().orc_octo_raycast(self.h, submap, n, _p(pos), _p(direction), float(max_dist), _p(hit), _p(xyz), _p(ln))
+        return hit.astype(bool), xyz, ln
 
 
 def integrate_stream_mt(maps, depth_frames, Rs, Ts):

@@ -928,6 +928,93 @@ void orc_octo_fuse(void* hdst, void* hsrc) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Map queries (BaseMap @ti.func helpers, mapping_common.py:165-204; DenseTSDF.is_occupy / is_unobserved,
+// dense_tsdf.py:148-155: TSDF < 1.8*vs with NO observed test - inactive cells read 0, i.e. "occupied").
+// ---------------------------------------------------------------------------
+static void tsdf_probe(Tsdf* m, int s, float x, float y, float z, bool& occ, bool& unobs) {
+  const float vs = m->vs;
+  const int i = iround(x / vs), j = iround(y / vs), k = iround(z / vs);
+  float t = 0.0f;
+  int o = 0;
+  if (m->in_bounds(i, j, k)) { t = m->readT(s, i, j, k); o = m->readObs(s, i, j, k); }
+  occ = t < (float)(m->c.voxel_scale * 1.8);
+  unobs = o == 0;
+}
+void orc_tsdf_query_points(void* h, int submap, int64_t n, const float* xyz, uint8_t* flags) {
+  Tsdf* m = (Tsdf*)h;
+  for (int64_t q = 0; q < n; q++) {
+    bool occ, un;
+    tsdf_probe(m, submap, xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2], occ, un);
+    flags[q] = (uint8_t)((occ ? 1 : 0) | (un ? 2 : 0));
+  }
+}
+void orc_tsdf_query_near(void* h, int submap, int64_t n, const float* xyz, int voxel, uint8_t* out) {  // mapping_common.py:193-204
+  Tsdf* m = (Tsdf*)h;
+  const float vs = m->vs;
+  for (int64_t q = 0; q < n; q++) {
+    const int i0 = iround(xyz[3 * q] / vs), j0 = iround(xyz[3 * q + 1] / vs), k0 = iround(xyz[3 * q + 2] / vs);
+    bool any = false;
+    for (int i = -voxel; i < voxel; i++)
+      for (int j = -voxel; j < voxel; j++)
+        for (int k = -voxel; k < voxel; k++) {
+          float t = 0.0f;
+          if (m->in_bounds(i0 + i, j0 + j, k0 + k)) t = m->readT(submap, i0 + i, j0 + j, k0 + k);
+          if (t < (float)(m->c.voxel_scale * 1.8)) any = true;
+        }
+    out[q] = any ? 1 : 0;
+  }
+}
+void orc_tsdf_raycast(void* h, int submap, int64_t n, const float* pos, const float* dir, float max_dist, uint8_t* hit, float* xyz_out,
+                      float* len_out) {  // mapping_common.py:165-178
+  Tsdf* m = (Tsdf*)h;
+  const float vs = m->vs;
+  for (int64_t q = 0; q < n; q++) {
+    const int steps = (int)(max_dist / vs);
+    float x = 0.f, y = 0.f, z = 0.f, len = 0.f;
+    bool succ = false;
+    for (int j = 0; j < steps; j++) {
+      len = (float)j * vs;
+      x = dir[3 * q] * len + pos[3 * q]; y = dir[3 * q + 1] * len + pos[3 * q + 1]; z = dir[3 * q + 2] * len + pos[3 * q + 2];
+      bool occ, un;
+      tsdf_probe(m, submap, x, y, z, occ, un);
+      if (occ) { succ = true; break; }
+    }
+    hit[q] = succ ? 1 : 0;
+    xyz_out[3 * q] = x; xyz_out[3 * q + 1] = y; xyz_out[3 * q + 2] = z;
+    len_out[q] = len;
+  }
+}
+static bool octo_probe(Octo* m, int s, float x, float y, float z) {  // taichi_octomap.py:86-88
+  const float vs = m->vs;
+  const int i = iround(x / vs), j = iround(y / vs), k = iround(z / vs);
+  uint32_t c = 0;
+  if (m->in_bounds(i, j, k)) { auto it = m->cnt.find(Key{s, i, j, k}); if (it != m->cnt.end()) c = it->second; }
+  return (float)c > (float)m->min_occupy_thres;
+}
+void orc_octo_query_points(void* h, int submap, int64_t n, const float* xyz, uint8_t* flags) {
+  Octo* m = (Octo*)h;
+  for (int64_t q = 0; q < n; q++) flags[q] = octo_probe(m, submap, xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]) ? 1 : 0;
+}
+void orc_octo_raycast(void* h, int submap, int64_t n, const float* pos, const float* dir, float max_dist, uint8_t* hit, float* xyz_out,
+                      float* len_out) {
+  Octo* m = (Octo*)h;
+  const float vs = m->vs;
+  for (int64_t q = 0; q < n; q++) {
+    const int steps = (int)(max_dist / vs);
+    float x = 0.f, y = 0.f, z = 0.f, len = 0.f;
+    bool succ = false;
+    for (int j = 0; j < steps; j++) {
+      len = (float)j * vs;
+      x = dir[3 * q] * len + pos[3 * q]; y = dir[3 * q + 1] * len + pos[3 * q + 1]; z = dir[3 * q + 2] * len + pos[3 * q + 2];
+      if (octo_probe(m, submap, x, y, z)) { succ = true; break; }
+    }
+    hit[q] = succ ? 1 : 0;
+    xyz_out[3 * q] = x; xyz_out[3 * q + 1] = y; xyz_out[3 * q + 2] = z;
+    len_out[q] = len;
+  }
+}
+
 // ----------------------------------------------------------------------------
 // CPU-baseline helper (bench.py `cpu_baseline` / `--impl reference`): integrate a
 // stream of frames with `nthreads` host threads, thread t owning map handles[t]

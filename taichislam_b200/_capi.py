@@ -74,6 +74,11 @@ SIGNATURES = {
     "tslam_tsdf_launch_count": (_i64, [_vp]),
     "tslam_tsdf_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tslam_tsdf_kernel_ms": (C.c_int, [_vp, _i32, _vp, C.POINTER(_i32)]),
+    "tslam_tsdf_query_points": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
+    "tslam_tsdf_query_near_occupy": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "tslam_tsdf_raycast": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "tslam_octo_query_points": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
+    "tslam_octo_raycast": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "tslam_tsdf_fuse_pending": (C.c_int, [_vp, _vp, _vp]),
     "tslam_tsdf_commit_fused": (C.c_int, [_vp, _vp]),
     "tslam_tiling_owner": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_i32)]),

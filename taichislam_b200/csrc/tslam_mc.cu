@@ -364,10 +364,9 @@ extern "C" int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float thres, int
   unsigned long long total = 0;
   unsigned long long* d_total = (unsigned long long*)(m->scratch_i + 10);
   if (step == 1) {
-    unsigned int* blk_tris = nullptr;
-    unsigned long long* blk_off = nullptr;
-    TS_CUDA(cudaMallocAsync((void**)&blk_tris, (size_t)m->g.max_blocks * 4, st));
-    TS_CUDA(cudaMallocAsync((void**)&blk_off, (size_t)m->g.max_blocks * 8, st));
+    if (!m->mc_scratch) TS_CUDA(cudaMalloc(&m->mc_scratch, (size_t)m->g.max_blocks * 12));  // persistent: per-block counts + offsets
+    unsigned long long* blk_off = (unsigned long long*)m->mc_scratch;
+    unsigned int* blk_tris = (unsigned int*)(blk_off + m->g.max_blocks);
     k_mc_count<<<m->sm_count * 4, 256, 0, st>>>(m->g, thres, blk_tris);
     TS_LAUNCH_CHECK(m);
     k_mc_scan<<<1, 1024, 0, st>>>(m->g.n_blocks, m->g.max_blocks, blk_tris, blk_off, d_total);
@@ -375,8 +374,6 @@ extern "C" int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float thres, int
     k_mc_emit<<<m->sm_count * 4, 256, 0, st>>>(m->g, thres, m->in.vs, blk_tris, blk_off, cap_tri, verts, normals);
     TS_LAUNCH_CHECK(m);
     TS_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
-    TS_CUDA(cudaFreeAsync(blk_tris, st));
-    TS_CUDA(cudaFreeAsync(blk_off, st));
     TS_CUDA(cudaStreamSynchronize(st));
   } else {
     TS_CUDA(cudaMemsetAsync(d_total, 0, 8, st));

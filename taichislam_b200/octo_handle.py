@@ -104,6 +104,25 @@ class OctoHandle:
         n = int(cnt.item())
         return n, xyz[:min(n, cap)].cpu().numpy()
 
+    def query_points(self, xyz, submap=0):
+        torch = self.torch
+        x = torch.from_numpy(np.ascontiguousarray(xyz, dtype=np.float32)).cuda()
+        f = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+        capi.check(self.L.tslam_octo_query_points(self.h, int(submap), x.shape[0], capi.tptr(x), capi.tptr(f), capi.stream_ptr()))
+        return f.cpu().numpy().astype(bool)
+
+    def raycast(self, pos, direction, max_dist, submap=0):
+        torch = self.torch
+        p = torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float32)).cuda()
+        d = torch.from_numpy(np.ascontiguousarray(direction, dtype=np.float32)).cuda()
+        n = p.shape[0]
+        hit = torch.empty(n, dtype=torch.uint8, device=p.device)
+        xyz = torch.empty((n, 3), dtype=torch.float32, device=p.device)
+        ln = torch.empty(n, dtype=torch.float32, device=p.device)
+        capi.check(self.L.tslam_octo_raycast(self.h, int(submap), n, capi.tptr(p), capi.tptr(d), float(max_dist), capi.tptr(hit), capi.tptr(xyz),
+                                             capi.tptr(ln), capi.stream_ptr()))
+        return hit.cpu().numpy().astype(bool), xyz.cpu().numpy(), ln.cpu().numpy()
+
     def fuse_from(self, src):
         capi.check(self.L.tslam_octo_fuse(self.h, src.h, capi.stream_ptr()))
 

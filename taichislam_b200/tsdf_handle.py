@@ -183,6 +183,41 @@ class TsdfHandle:
         k = min(int(n.value), cap_tri)
         return int(n.value), v[:3 * k].cpu().numpy(), nrm[:3 * k].cpu().numpy()
 
+    # -- planner queries (batched @ti.func helpers of BaseMap, mapping_common.py:165-204) ------------------
+    def _dev_f32(self, a):
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            return a.to(device="cuda", dtype=torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+    def query_points(self, xyz, submap=0):
+        """(is_pos_occupy, is_pos_unobserved) per point."""
+        torch = self.torch
+        x = self._dev_f32(xyz)
+        f = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+        capi.check(self.L.tslam_tsdf_query_points(self.h, int(submap), x.shape[0], capi.tptr(x), capi.tptr(f), capi.stream_ptr()))
+        f = f.cpu().numpy()
+        return (f & 1).astype(bool), (f & 2).astype(bool)
+
+    def query_near_occupy(self, xyz, voxel, submap=0):
+        torch = self.torch
+        x = self._dev_f32(xyz)
+        f = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+        capi.check(self.L.tslam_tsdf_query_near_occupy(self.h, int(submap), x.shape[0], capi.tptr(x), int(voxel), capi.tptr(f), capi.stream_ptr()))
+        return f.cpu().numpy().astype(bool)
+
+    def raycast(self, pos, direction, max_dist, submap=0):
+        """BaseMap.raycast for a batch of rays: (hit, last position, length)."""
+        torch = self.torch
+        p, d = self._dev_f32(pos), self._dev_f32(direction)
+        n = p.shape[0]
+        hit = torch.empty(n, dtype=torch.uint8, device=p.device)
+        xyz = torch.empty((n, 3), dtype=torch.float32, device=p.device)
+        ln = torch.empty(n, dtype=torch.float32, device=p.device)
+        capi.check(self.L.tslam_tsdf_raycast(self.h, int(submap), n, capi.tptr(p), capi.tptr(d), float(max_dist), capi.tptr(hit), capi.tptr(xyz),
+                                             capi.tptr(ln), capi.stream_ptr()))
+        return hit.cpu().numpy().astype(bool), xyz.cpu().numpy(), ln.cpu().numpy()
+
     def esdf_update(self, submap=0):
         sw = C.c_int32(0)
         capi.check(self.L.tslam_esdf_update(self.h, int(submap), C.byref(sw), capi.stream_ptr()))

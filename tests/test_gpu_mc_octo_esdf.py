@@ -193,3 +193,43 @@ def test_esdf_matches_dijkstra_oracle():
     o.esdf_update()
     _, oe1 = as_dict_rows(*o.esdf_gather())
     assert np.quantile(np.abs(ee - oe1), 0.999) <= 1e-4
+
+
+def test_planner_queries_match_oracle():
+    """Batched raycast / is_pos_occupy / is_pos_unobserved / is_near_pos_occupy (mapping_common.py:165-204), bit-exact."""
+    from oracle.oracle import OracleTSDF, OracleOctomap
+    from taichislam_b200.tsdf_handle import TsdfHandle
+    from taichislam_b200.octo_handle import OctoHandle
+    o = OracleTSDF(map_scale=[12.8, 12.8], K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    g = TsdfHandle(o.N, o.Nz, K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    d = syn.scene_room()
+    g.integrate_depth(d, np.eye(3)[None], np.zeros((1, 3)))
+    gi, gt, gw, gocc = g.gather()
+    o.scatter(0, gi, gt, gw, gocc)  # identical TSDF values on both sides
+    rng = np.random.default_rng(3)
+    pts = rng.uniform([-3, -2, -0.5], [3, 2, 5.5], size=(20000, 3)).astype(np.float32)
+    pts[:10] = 100.0  # outside the volume
+    go, gu = g.query_points(pts)
+    oo, ou = o.query_points(pts)
+    assert np.array_equal(go, oo) and np.array_equal(gu, ou) and 0.05 < (~gu).mean() < 0.95
+    assert np.array_equal(g.query_near_occupy(pts[:3000], 2), o.query_near_occupy(pts[:3000], 2))
+    # rays from observed free space (inside the scanned cone) in random directions
+    free = pts[(~gu) & (~go)][:4000]
+    dirs = rng.normal(size=free.shape).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    gh, gx, gl = g.raycast(free, dirs, 3.0)
+    oh, ox, ol = o.raycast(free, dirs, 3.0)
+    assert np.array_equal(gh, oh) and np.array_equal(gx, ox) and np.array_equal(gl, ol) and gh.mean() > 0.5
+    # octomap
+    oo_ = OracleOctomap(map_scale=[12.8, 12.8], voxel_scale=0.05, K=2, min_occupy_thres=0, max_ray_length=6.0, Kcam=syn.K_DEPTH)
+    og = OctoHandle(oo_.N, oo_.Nz, K=2, voxel_scale=0.05, min_occupy_thres=0, max_ray_length=6.0, Kcam=syn.K_DEPTH)
+    og.integrate_depth(d, np.eye(3), np.zeros(3))
+    oo_.integrate_depth(np.eye(3), np.zeros(3), d)
+    assert np.array_equal(og.query_points(pts), oo_.query_points(pts))
+    origin = np.zeros((2000, 3), np.float32)
+    dirs = rng.normal(size=origin.shape).astype(np.float32)
+    dirs[:, 2] = np.abs(dirs[:, 2]) + 0.5
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    a = og.raycast(origin, dirs, 6.0)
+    b = oo_.raycast(origin, dirs, 6.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[0].any()

@@ -216,37 +216,60 @@ static void fill_jet(float cm[1024][3]) {
 // ---------------------------------------------------------------------------
 // Per-frame bucket grid  (dense_tsdf.py:64-70: new_pcl_count i32,
 // new_pcl_sum_pos 3xf16, new_pcl_z f16; keyed by round(p/vs)).
-// std::map => lexicographic (i,j,k) iteration = the canonical bucket order.
+// Points are appended in pixel order; finalize() stable-sorts them by cell and folds every cell's points in
+// that (pixel) order, so iteration is lexicographic in (i,j,k) = the canonical bucket order, exactly what a
+// std::map keyed by the cell would give - without one heap node per cell (the multi-threaded CPU baseline
+// spent its time in malloc).
 // ---------------------------------------------------------------------------
 struct Bucket {
   int count = 0;
   int64_t fx = 0, fy = 0, fz = 0, fd = 0;  // canonical exact sums
   float sx = 0, sy = 0, sz = 0, sd = 0;    // literal float sums (f32 or f16-rounded)
 };
-typedef std::map<std::array<int, 3>, Bucket> BucketGrid;
+struct BucketGrid {
+  struct Raw { std::array<int, 3> key; float p[3]; float z; };
+  std::vector<Raw> raw;
+  std::vector<std::pair<std::array<int, 3>, Bucket>> cells;
+  void finalize(int mode) {
+    std::vector<uint32_t> ord(raw.size());
+    for (uint32_t i = 0; i < ord.size(); i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return raw[a].key < raw[b].key; });
+    cells.clear();
+    for (uint32_t o : ord) {
+      const Raw& r = raw[o];
+      if (cells.empty() || cells.back().first != r.key) cells.emplace_back(r.key, Bucket());
+      Bucket& q = cells.back().second;
+      q.count += 1;
+      if (mode == MODE_CANONICAL) {
+        q.fx += llrintf(r.p[0] * (float)FIX);
+        q.fy += llrintf(r.p[1] * (float)FIX);
+        q.fz += llrintf(r.p[2] * (float)FIX);
+        q.fd += llrintf(r.z * (float)FIX);
+      } else if (mode == MODE_F32_LITERAL) {
+        q.sx += r.p[0];
+        q.sy += r.p[1];
+        q.sz += r.p[2];
+        q.sd += r.z;
+      } else {  // f16 atomic add: operand cast to f16, sum rounded to f16
+        q.sx = h16(q.sx + h16(r.p[0]));
+        q.sy = h16(q.sy + h16(r.p[1]));
+        q.sz = h16(q.sz + h16(r.p[2]));
+        q.sd = h16(q.sd + h16(r.z));
+      }
+    }
+  }
+  std::vector<std::pair<std::array<int, 3>, Bucket>>::iterator begin() { return cells.begin(); }
+  std::vector<std::pair<std::array<int, 3>, Bucket>>::iterator end() { return cells.end(); }
+};
 
 // process_point  (dense_tsdf.py:227-234)
 static void bucket_add(const Tsdf& m, BucketGrid& g, const float p[3], float z) {
   const float vs = m.vs;
-  std::array<int, 3> b = {iround(p[0] / vs), iround(p[1] / vs), iround(p[2] / vs)};  // xyz_to_ijk mapping_common.py:240-243
-  Bucket& q = g[b];
-  q.count += 1;
-  if (m.c.mode == MODE_CANONICAL) {
-    q.fx += llrintf(p[0] * (float)FIX);
-    q.fy += llrintf(p[1] * (float)FIX);
-    q.fz += llrintf(p[2] * (float)FIX);
-    q.fd += llrintf(z * (float)FIX);
-  } else if (m.c.mode == MODE_F32_LITERAL) {
-    q.sx += p[0];
-    q.sy += p[1];
-    q.sz += p[2];
-    q.sd += z;
-  } else {  // f16 atomic add: operand cast to f16, sum rounded to f16
-    q.sx = h16(q.sx + h16(p[0]));
-    q.sy = h16(q.sy + h16(p[1]));
-    q.sz = h16(q.sz + h16(p[2]));
-    q.sd = h16(q.sd + h16(z));
-  }
+  BucketGrid::Raw r;
+  r.key = {iround(p[0] / vs), iround(p[1] / vs), iround(p[2] / vs)};  // xyz_to_ijk mapping_common.py:240-243
+  r.p[0] = p[0]; r.p[1] = p[1]; r.p[2] = p[2];
+  r.z = z;
+  g.raw.push_back(r);
 }
 
 static inline void rot(const float R[9], const float v[3], float o[3]) {  // input_R[None] @ pt
@@ -260,6 +283,7 @@ static void raymarch(Tsdf& m, BucketGrid& g, const float Tin[3], int s) {
   const float vs = m.vs;
   const int mode = m.c.mode;
   const float max_steps = (float)(m.c.max_ray_length / m.c.voxel_scale);  // python-float constant, dense_tsdf.py:249
+  g.finalize(mode);
   for (auto& kv : g) {
     Bucket& q = kv.second;
     if (q.count == 0) continue;  // :240
@@ -299,6 +323,8 @@ static void raymarch(Tsdf& m, BucketGrid& g, const float Tin[3], int s) {
     float w;
     if (mode == MODE_F16_FAITHFUL) w = 1.0f / h16(z * z); else w = 1.0f / (z * z);  // w_x_p :216-225 with d>=0
     float jf = 0.0f;
+    Block* last_b = nullptr;
+    Key last_key{0, 0, 0, 0};
     for (int it = 0; it < n; it++) {
       jf += 1.0f;  // :252
       float x = (ux * jf) * vs + Tin[0], y = (uy * jf) * vs + Tin[1], zz = (uz * jf) * vs + Tin[2];  // :253
@@ -308,7 +334,12 @@ static void raymarch(Tsdf& m, BucketGrid& g, const float Tin[3], int s) {
       float ds = d * (float)sgn((vx * mx + vy * my) + vz * mz);  // :260
       if (!m.in_bounds(xi, yi, zi)) { m.st.n_oob++; continue; }
       m.st.n_updates++;
-      int o; Block* b = m.touch(s, xi, yi, zi, &o);
+      int o; Block* b;
+      {  // consecutive samples of a ray mostly stay in one block: skip the hash lookup then
+        const Key bk{s, fdiv(xi, OB), fdiv(yi, OB), fdiv(zi, OB)};
+        if (last_b && bk == last_key) { b = last_b; o = (fmod_(xi, OB) * OB + fmod_(yi, OB)) * OB + fmod_(zi, OB); }
+        else { b = m.touch(s, xi, yi, zi, &o); last_b = b; last_key = bk; }
+      }
       if (mode == MODE_CANONICAL) {
         if (!b->pending) { b->pending = true; m.dirty.push_back(b); }
         b->A[o] += (double)(w * ds);

@@ -253,3 +253,24 @@ def test_full_size_properties_512():
     assert g.stats()["n_updates"] == 2 * st1["n_updates"]
     g.reset()
     assert g.count_active() == 0
+
+
+def test_block_axis_10_and_long_range_config():
+    """SubmapMapping's default num_voxel_per_blk_axis=10 (N not a multiple of the internal 16^3 block) and a
+    max_ray_length >= 60 m configuration (per-pixel reductions instead of the warp-merged ones in the bucket kernel)."""
+    d = syn.scene_room()
+    R = rot_xyz(0.05, 0.1, -0.2)
+    T = np.array([0.1, 0.05, 0.0])
+    g, o = make_pair([10, 10], is_global_map=True, num_voxel_per_blk_axis=10)
+    assert o.N == 200
+    g.integrate_depth(d, R[None], T[None])
+    o.integrate_depth(R, T, d)
+    stats_equal(g, o)
+    assert o.stats()["n_oob"] > 0
+    compare_voxels(g.gather(), o.gather(), TOL)
+    far = (syn.scene_room().astype(np.float32) * 10).clip(0, 65000).astype(np.uint16)  # up to 50 m
+    g2, o2 = make_pair([102.4, 102.4], is_global_map=True, max_ray_length=64.0, voxel_scale=0.2)
+    g2.integrate_depth(far, R[None], T[None])
+    o2.integrate_depth(R, T, far)
+    stats_equal(g2, o2)
+    compare_voxels(g2.gather(), o2.gather(), 2e-4)  # values up to 64 m: f32 resolution itself is 4e-6 there

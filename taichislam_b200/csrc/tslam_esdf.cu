@@ -12,26 +12,43 @@
 //     negative side: E(v) = max(E(v), E(h) - |dir|*vs)   h in fixed U negative   (:294-298)
 //   to convergence.  f32 min/+ is monotone, so the least fixed point is unique and
 //   equals the oracle's multi-source Dijkstra bit-for-bit.
-// Implementation: block-parallel wavefront.  Each sweep a CTA stages its block plus a
-// one-voxel halo (18^3) in shared memory, relaxes to LOCAL convergence with
-// ballot-voted iteration, writes back and raises a global "changed" flag; sweeps repeat
-// until no block changes (the wave crosses one block boundary per sweep).
+// Implementation: block-parallel wavefront with a block-level WORK QUEUE.
+//   * a CTA stages its block plus a one-voxel halo (18^3) in shared memory, relaxes to
+//     LOCAL convergence (ballot-voted iterations), writes back and stamps the block
+//     with the sweep number when anything changed;
+//   * sweep k only runs the blocks that have a neighbour (26 + self) stamped >= k-1 -
+//     the wave front; every block's 27 neighbour indices are resolved once per update;
+//   * sweeps are enqueued in groups; a sweep whose predecessor changed nothing returns
+//     at once, so the host only synchronises once per group to test for convergence.
 #include <cstring>
 #include "tslam_internal.cuh"
 
 #define ES_T 18
 #define ES_T3 (ES_T * ES_T * ES_T)
+#define ES_GROUP 6       // sweeps enqueued per host synchronisation
+#define ES_MAX_SWEEPS 4096
 
 enum { ES_UNOBS = 0, ES_FIXED = 1, ES_POS = 2, ES_NEG = 3, ES_INERT = 4 };  // INERT: observed, TSDF is NaN
 
+struct EsAux {
+  int* nbr;      // [max_blocks*27] neighbour block indices (-1 = absent)
+  int* epoch;    // [max_blocks] last sweep in which the block changed
+  int* changed;  // [ES_MAX_SWEEPS+2] changed[k] != 0 <=> sweep k changed something
+};
+
 __device__ __forceinline__ float es_sgn(float v) { return (float)((0.0f < v) - (v < 0.0f)); }
 
-__global__ void __launch_bounds__(256) k_esdf_init(TsGrid g, int submap, float gamma, float far_v) {
+__global__ void __launch_bounds__(256) k_esdf_init(TsGrid g, EsAux aux, int submap, float gamma, float far_v) {
   const int nb = min(*g.n_blocks, g.max_blocks);
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
     ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    if (threadIdx.x == 0) aux.epoch[b] = (s == submap) ? 0 : -1000000;
     if (s != submap) continue;
+    if (threadIdx.x < 27) {
+      const int dx = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x % 3 - 1;
+      aux.nbr[b * 27 + threadIdx.x] = ts_find(g, ts_pack_key(s, bx + dx, by + dy, bz + dz));
+    }
     const size_t base = (size_t)b * TS_B3;
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       float e = 0.0f;
@@ -48,27 +65,30 @@ struct EsTile {
   float e[ES_T3];
   unsigned char cls[ES_T3];
   int nbr[27];
+  int active;
   int changed;
   int any_write;
 };
 
 __device__ __forceinline__ int es_tidx(int lx, int ly, int lz) { return ((lx + 1) * ES_T + (ly + 1)) * ES_T + (lz + 1); }
 
-__global__ void __launch_bounds__(256) k_esdf_sweep(TsGrid g, int submap, float gamma, float vs, int* changed_flag) {
+__global__ void __launch_bounds__(256) k_esdf_sweep(TsGrid g, EsAux aux, int submap, int sweep, float gamma, float vs) {
   __shared__ EsTile tile;
+  if (sweep > 1 && aux.changed[sweep - 1] == 0) return;  // already converged: nothing to do
   const int nb = min(*g.n_blocks, g.max_blocks);
   const float d1 = vs, d2 = sqrtf(2.0f) * vs, d3 = sqrtf(3.0f) * vs;  // dir.norm()*voxel_scale (dense_esdf.py:285)
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-    int s, bx, by, bz;
-    ts_unpack_key(g.block_key[b], s, bx, by, bz);
-    if (s != submap) continue;
     __syncthreads();
+    if (threadIdx.x == 0) { tile.active = 0; tile.any_write = 0; }
+    __syncthreads();
+    if (aux.epoch[b] < -1) continue;  // block of another submap (uniform per CTA)
     if (threadIdx.x < 27) {
-      const int dx = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x % 3 - 1;
-      tile.nbr[threadIdx.x] = ts_find(g, ts_pack_key(s, bx + dx, by + dy, bz + dz));
+      const int n = aux.nbr[b * 27 + threadIdx.x];
+      tile.nbr[threadIdx.x] = n;
+      if (n >= 0 && *(volatile int*)&aux.epoch[n] >= sweep - 1) tile.active = 1;  // the wave front reaches this block
     }
-    if (threadIdx.x == 0) tile.any_write = 0;
     __syncthreads();
+    if (!tile.active) continue;
     for (int c = threadIdx.x; c < ES_T3; c += blockDim.x) {
       const int lz = c % ES_T - 1, ly = (c / ES_T) % ES_T - 1, lx = c / (ES_T * ES_T) - 1;
       const int nx = (lx + 16) >> 4, ny = (ly + 16) >> 4, nz = (lz + 16) >> 4;
@@ -80,7 +100,7 @@ __global__ void __launch_bounds__(256) k_esdf_sweep(TsGrid g, int submap, float 
         if (g.obs[off]) {
           const float t = g.tw[off].x;
           cl = (fabsf(t) < gamma) ? ES_FIXED : (t > 0.0f ? ES_POS : (t < 0.0f ? ES_NEG : ES_INERT));
-          ev = g.esdf[off];
+          ev = *(volatile float*)&g.esdf[off];
         }
       }
       tile.e[c] = ev;
@@ -129,7 +149,11 @@ __global__ void __launch_bounds__(256) k_esdf_sweep(TsGrid g, int submap, float 
     if (tile.any_write) {
       const size_t base = (size_t)b * TS_B3;
       for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) g.esdf[base + v] = tile.e[es_tidx(v >> 8, (v >> 4) & 15, v & 15)];
-      if (threadIdx.x == 0) atomicExch(changed_flag, 1);
+      if (threadIdx.x == 0) {
+        __threadfence();
+        aux.epoch[b] = sweep;
+        aux.changed[sweep] = 1;
+      }
     }
   }
 }
@@ -169,24 +193,36 @@ extern "C" int tslam_esdf_update(tslam_tsdf_t* m, int32_t submap, int32_t* n_swe
   if (!m->g.esdf) {
     TS_CUDA(cudaMalloc(&m->g.esdf, (size_t)m->g.max_blocks * TS_B3 * 4));
     TS_CUDA(cudaMemset(m->g.esdf, 0, (size_t)m->g.max_blocks * TS_B3 * 4));
+    TS_CUDA(cudaMalloc(&m->esdf_aux, ((size_t)m->g.max_blocks * 28 + ES_MAX_SWEEPS + 2) * 4));
   }
+  EsAux aux;
+  aux.nbr = (int*)m->esdf_aux;
+  aux.epoch = aux.nbr + (size_t)m->g.max_blocks * 27;
+  aux.changed = aux.epoch + m->g.max_blocks;
   const float gamma = (float)m->cfg.voxel_scale;     // dense_esdf.py:40
   const float far_v = (float)m->cfg.max_ray_length;  // dense_esdf.py:324
-  k_esdf_init<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, gamma, far_v);
+  TS_CUDA(cudaMemsetAsync(aux.changed, 0, (ES_MAX_SWEEPS + 2) * 4, st));
+  k_esdf_init<<<m->sm_count * 4, 256, 0, st>>>(m->g, aux, submap, gamma, far_v);
   TS_LAUNCH_CHECK(m);
-  int* flag = m->scratch_i + 12;
   int sweeps = 0;
   for (;;) {
-    TS_CUDA(cudaMemsetAsync(flag, 0, 4, st));
-    k_esdf_sweep<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, gamma, m->in.vs, flag);
-    TS_LAUNCH_CHECK(m);
-    sweeps++;
+    for (int q = 0; q < ES_GROUP && sweeps < ES_MAX_SWEEPS; q++) {
+      sweeps++;
+      k_esdf_sweep<<<m->sm_count * 4, 256, 0, st>>>(m->g, aux, submap, sweeps, gamma, m->in.vs);
+      TS_LAUNCH_CHECK(m);
+    }
     int changed = 0;
-    TS_CUDA(cudaMemcpyAsync(&changed, flag, 4, cudaMemcpyDeviceToHost, st));
+    TS_CUDA(cudaMemcpyAsync(&changed, aux.changed + sweeps, 4, cudaMemcpyDeviceToHost, st));
     TS_CUDA(cudaStreamSynchronize(st));
-    if (!changed || sweeps > 4096) break;
+    if (!changed || sweeps >= ES_MAX_SWEEPS) break;
   }
-  if (n_sweeps_out) *n_sweeps_out = sweeps;
+  if (n_sweeps_out) {  // sweeps the wave needed: the first sweep that changed nothing ends it
+    static int h_changed[ES_MAX_SWEEPS + 2];
+    TS_CUDA(cudaMemcpy(h_changed, aux.changed, (size_t)(sweeps + 1) * 4, cudaMemcpyDeviceToHost));
+    int k = 1;
+    while (k <= sweeps && h_changed[k]) k++;
+    *n_sweeps_out = k;
+  }
   return TSLAM_OK;
 }
 

@@ -214,6 +214,7 @@ struct tslam_tsdf {
   float* pose_T;       // [max_submaps*3]
   float* colormap;     // device jet LUT [1024*3]
   int* scratch_i;      // small device scratch (counters for gather etc.)
+  void* esdf_aux;      // ESDF: neighbour table, epochs, per-sweep change flags (allocated with g.esdf)
   void* mc_scratch;    // marching cubes: per-block triangle counts / offsets (allocated on first use)
   long long launches;
   int n_integrate_calls;

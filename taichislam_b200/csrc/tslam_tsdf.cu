@@ -730,6 +730,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   TsGrid& g = m->g;
   cudaFree(g.table); cudaFree(g.block_key); cudaFree(g.acc); cudaFree(g.tw); cudaFree(g.obs); cudaFree(g.occ);
   if (g.esdf) cudaFree(g.esdf);
+  if (m->esdf_aux) cudaFree(m->esdf_aux);
   if (m->mc_scratch) cudaFree(m->mc_scratch);
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);

@@ -159,7 +159,7 @@ __device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_bas
 // row per thread, :192-194); a warp covers an 8x4 tile of sampled pixels, a CTA 32x8;
 // blockIdx.z = frame of the batch.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int h, int w, int hh, int ww,
+__global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int frame_stride, int row_mul, int w, int hh, int ww,
                                                        const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
                                                        TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
                                                        int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
   float px = 0.f, py = 0.f, pz = 0.f, dep = 0.f;
   if (ii < ww && jj < hh) {
     const int j = jj * in.step, i = ii * in.step;
-    const uint16_t d = depth[(size_t)f * h * w + (size_t)j * w + i];
+    // row_mul = recast_step for full frames, 1 when the staging copy already dropped the unsampled rows
+    const uint16_t d = depth[(size_t)f * frame_stride + (size_t)(jj * row_mul) * w + i];
     const float df = (float)d;
     if (d != 0 && !(df > in.dmax_mm || df < in.dmin_mm)) {  // :196-199
       valid = true;
@@ -835,8 +836,16 @@ static void ts_fill_frame(TsFrame& fr, const float* R9, const float* T3, int sub
   fr.submap = submap;
 }
 
+static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
+                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted);
 extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                           const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream) {
+  return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0);
+}
+// rows_compacted: the frames hold only the sampled rows (hh = h/step rows of w pixels each) - the per-frame queue
+// stages them that way with a strided 2-D copy, halving the host->device bytes for recast_step 2.
+static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
+                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted) {
   if (!m || !depth || !R9s || !T3s || n_frames < 0 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
   if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -853,7 +862,8 @@ extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth
       if (sid < 0 || sid >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", sid); return TSLAM_E_INVALID; }
       ts_fill_frame(batch.f[q], R9s + 9 * (size_t)(base + q), T3s + 3 * (size_t)(base + q), sid);
     }
-    const uint16_t* src = depth + (size_t)base * h * w;
+    const int rows_stored = rows_compacted ? hh : h;
+    const uint16_t* src = depth + (size_t)base * rows_stored * w;
     if (mem == TSLAM_MEM_HOST) {
       TS_CUDA(cudaMemcpyAsync(m->depth_stage, src, (size_t)nf * h * w * 2, cudaMemcpyHostToDevice, st));
       src = m->depth_stage;
@@ -862,7 +872,7 @@ extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
     dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
     const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
-    k_bucket_depth<<<grid1, 256, 0, st>>>(src, h, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
+    k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
                                           m->n_rays, m->ray_list_cap, m->counters, m->g.err);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
@@ -935,7 +945,7 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   const uint16_t* src = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels;
   m->q_n = 0;  // (integrate may recurse into flush through readers; the queue is empty from here on)
   m->q_buf = b ^ 1;
-  int rc = tslam_tsdf_integrate_depth(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st);
+  int rc = ts_integrate_depth_impl(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st, 1);
   if (rc) return rc;
   TS_CUDA(cudaEventRecord(m->ev_free[b], st));
   m->ev_free_valid[b] = true;
@@ -962,8 +972,13 @@ extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_hos
     m->q_h = h; m->q_w = w;
     if (m->ev_free_valid[b]) TS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_free[b], 0));  // kernels that read this buffer are done
   }
-  uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
-  TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  // only the sampled rows travel: a strided 2-D copy (source pitch = recast_step rows) into a compact hh x w frame
+  const int step = m->cfg.recast_step;
+  const int hh = (int)((double)h / step);
+  uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * hh * w;
+  if (hh > 0)
+    TS_CUDA(cudaMemcpy2DAsync(dst, (size_t)w * 2, depth_host, (size_t)step * w * 2, (size_t)w * 2, (size_t)hh, cudaMemcpyHostToDevice,
+                              m->copy_stream));
   memcpy(m->q_R + 9 * q, R9, 36);
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;

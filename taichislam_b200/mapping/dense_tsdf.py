@@ -62,6 +62,8 @@ class DenseTSDF(BaseMap):
                              max_image_pixels=max_image_pixels)
         self.initialize_submap_fields(self.max_submap_num)
         self._init_export_fields()
+        self._queue = self._h.L.tslam_tsdf_queue_depth
+        self._pR, self._pT = self.input_R_np.ctypes.data, self.input_T_np.ctypes.data  # persistent pose buffers (BaseMap.set_pose)
         print(f"TSDF map initialized blocks {self.block_num_xy}x{self.block_num_xy}x{self.block_num_z}")
 
     # ------------------------------------------------------------------ fields (dense_tsdf.py:52-60, :129-134)
@@ -96,8 +98,7 @@ class DenseTSDF(BaseMap):
             depthmap = np.ascontiguousarray(depthmap, dtype=np.uint16)
         h, w = depthmap.shape
         sid = 0 if self.is_global_map else self.active_submap_id.v
-        rc = self._h.L.tslam_tsdf_queue_depth(self._h.h, depthmap.ctypes.data, h, w, self.input_R_np.ctypes.data,
-                                              self.input_T_np.ctypes.data, sid, self._stream_ptr())
+        rc = self._queue(self._h.h, depthmap.__array_interface__["data"][0], h, w, self._pR, self._pT, sid, self._stream_ptr())
         if rc:
             capi.check(rc)
 

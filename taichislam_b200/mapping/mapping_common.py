@@ -87,5 +87,6 @@ class BaseMap:
 
     def set_pose(self, _R, _T):  # :149-156
         _R, _T = self.convert_by_base(_R, _T)
-        self.input_R_np = np.ascontiguousarray(_R, dtype=np.float32)
-        self.input_T_np = np.ascontiguousarray(_T, dtype=np.float32)
+        # f64 -> f32 cast into persistent buffers (their addresses are handed to the C ABI every frame)
+        np.copyto(self.input_R_np, _R, casting="same_kind")
+        np.copyto(self.input_T_np, _T, casting="same_kind")

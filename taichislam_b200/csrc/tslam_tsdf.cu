@@ -945,7 +945,7 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   const uint16_t* src = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels;
   m->q_n = 0;  // (integrate may recurse into flush through readers; the queue is empty from here on)
   m->q_buf = b ^ 1;
-  int rc = ts_integrate_depth_impl(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st, 1);
+  int rc = ts_integrate_depth_impl(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st, 0);
   if (rc) return rc;
   TS_CUDA(cudaEventRecord(m->ev_free[b], st));
   m->ev_free_valid[b] = true;
@@ -972,13 +972,10 @@ extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_hos
     m->q_h = h; m->q_w = w;
     if (m->ev_free_valid[b]) TS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_free[b], 0));  // kernels that read this buffer are done
   }
-  // only the sampled rows travel: a strided 2-D copy (source pitch = recast_step rows) into a compact hh x w frame
-  const int step = m->cfg.recast_step;
-  const int hh = (int)((double)h / step);
-  uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * hh * w;
-  if (hh > 0)
-    TS_CUDA(cudaMemcpy2DAsync(dst, (size_t)w * 2, depth_host, (size_t)step * w * 2, (size_t)w * 2, (size_t)hh, cudaMemcpyHostToDevice,
-                              m->copy_stream));
+  // One linear copy of the whole frame.  (A strided 2-D copy of only the sampled rows halves the bytes but was
+  // measured SLOWER from pinned memory: 30.2 k vs 36.5 k frames/s end to end - 240 row descriptors of 1280 B.)
+  uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
+  TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
   memcpy(m->q_R + 9 * q, R9, 36);
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;

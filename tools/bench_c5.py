@@ -58,6 +58,7 @@ def main():
     mv, mn, counts = tiled.generate_mesh_all_gather(mesher)
     torch.cuda.synchronize(); dist.barrier()
     t_mesh = time.perf_counter() - t0
+    x.update(tiled.last_exchange)
     own = torch.tensor([glo.count_active(), sum(sub._h.count_active(s) for s in mine), x["fusion_blocks_sent"], x.get("halo_blocks_sent", 0),
                         glo._h.stats()["n_blocks"]], dtype=torch.float64, device="cuda")
     dist.all_reduce(own)

@@ -275,8 +275,10 @@ def main():
     try:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        ntri, _, _ = g.marching_cubes(1, 0.25, cap_tri=1 << 22)  # cold: first launch of the three MC kernels, output buffers allocated
+        t1 = time.perf_counter()
         ntri, _, _ = g.marching_cubes(1, 0.25, cap_tri=1 << 22)
-        mc = {"triangles": int(ntri), "ms_incl_d2h_of_mesh": 1e3 * (time.perf_counter() - t0)}
+        mc = {"triangles": int(ntri), "ms_incl_d2h_of_mesh": 1e3 * (time.perf_counter() - t1), "first_call_ms": 1e3 * (t1 - t0)}
     except Exception as ex:  # pragma: no cover
         mc = {"error": str(ex)}
 

@@ -45,7 +45,7 @@ const char* tslam_last_error(void);
 int tslam_device_count(void);
 /* ABI version of this header (tests check the library agrees). */
 int tslam_abi_version(void);
-#define TSLAM_ABI_VERSION 1
+#define TSLAM_ABI_VERSION 2
 
 /* ----------------------------------------------------------------------------
  * TSDF map  (DenseTSDF, dense_tsdf.py)
@@ -66,6 +66,7 @@ typedef struct tslam_tsdf_config {
   int32_t max_blocks;        /* capacity of the 16^3 voxel-block pool (0 = derive)   */
   int32_t max_image_pixels;  /* largest h*w a depth frame may have (0 = 640*480)     */
   int32_t max_points;        /* largest point cloud for integrate_points (0 = 1<<20) */
+  int32_t texture_enabled;   /* dense_tsdf.py:13 texture_enabled: colour planes + colour fusion        */
 } tslam_tsdf_config_t;
 
 /* DenseTSDF.__init__ / initialize_fields (dense_tsdf.py:13-118). */
@@ -97,6 +98,25 @@ int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, 
 int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
                            const float* T3, int32_t submap, void* stream);
 int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);
+/* Textured maps (texture_enabled).  set_color_camera_intrinsic (mapping_common.py:28-29) + color_same_proj
+ * (dense_tsdf.py:16).  The *_tex / *_rgb forms take the colour image uint8 [n_frames,th,tw,3] (channel order as
+ * given - DenseTSDF does not swap BGR) or per-point colours uint8 [n,3]; tex == NULL integrates geometry only.
+ * Colour semantics: the reference overwrites color[xi] at every sample, racing rays, last writer wins
+ * (dense_tsdf.py:268-269); here the winner is deterministic: latest frame, then the sample closest to its ray's
+ * surface point (DESIGN.md "Texture"). */
+int tslam_tsdf_set_color_intrinsics(tslam_tsdf_t* m, double fx, double fy, double cx, double cy, int color_same_proj);
+int tslam_tsdf_integrate_depth_tex(tslam_tsdf_t* m, const uint16_t* depth, const uint8_t* tex, int mem, int32_t n_frames, int32_t h,
+                                   int32_t w, int32_t th, int32_t tw, const float* R9s, const float* T3s, const int32_t* submap_ids,
+                                   int flags, void* stream);
+int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth_host, const uint8_t* tex_host, int32_t h, int32_t w, int32_t th,
+                               int32_t tw, const float* R9, const float* T3, int32_t submap, void* stream);
+int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz, const uint8_t* rgb, int mem, int32_t n, const float* R9,
+                                    const float* T3, int32_t submap, int flags, void* stream);
+/* to_numpy / load_numpy with the colour column (dense_tsdf.py:437-440, :450-453): color f32[cap,3] DEVICE or NULL. */
+int tslam_tsdf_gather2(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* tsdf, float* w, int8_t* occ, float* color,
+                       int64_t* n_out, void* stream);
+int tslam_tsdf_scatter2(tslam_tsdf_t* m, int32_t submap, int64_t n, const int32_t* idx, const float* tsdf, const float* w,
+                        const int8_t* occ, const float* color, void* stream);
 /* DenseTSDF.recast_pcl_to_map -> recast_pcl_to_map_kernel (dense_tsdf.py:157-160, :167-186).
  * xyz: float32 [n,3]. */
 int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
@@ -194,6 +214,10 @@ int tslam_tsdf_ghost_unpack(tslam_tsdf_t* m, int64_t n, const int64_t* keys, con
  * f32 [3*cap_tri,3]; *n_tri_out = true triangle demand (host).  Synchronises. */
 int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float tsdf_surface_thres, int64_t cap_tri, float* verts,
                       float* normals, int64_t* n_tri_out, void* stream);
+/* ... with vertex colours (vertexInterp_color / add_triangle_color, marching_cube_mesher.py:62-82, :104-108):
+ * colors f32[3*cap_tri,3] DEVICE or NULL. */
+int tslam_mc_generate2(tslam_tsdf_t* m, int32_t step, float tsdf_surface_thres, int64_t cap_tri, float* verts, float* normals,
+                       float* colors, int64_t* n_tri_out, void* stream);
 
 /* ----------------------------------------------------------------------------
  * ESDF  (DenseSDF.propogate_esdf semantics, dense_esdf.py:228-333)

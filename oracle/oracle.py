@@ -84,6 +84,14 @@ def lib():
         L.orc_octo_export.argtypes = [vp, i32, i32, i64, vp]
         L.orc_octo_export.restype = i64
         L.orc_octo_fuse.argtypes = [vp, vp]
+        L.orc_tsdf_set_color.argtypes = [vp, i32, i32, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_tsdf_integrate_depth_tex.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]
+        L.orc_tsdf_integrate_points_rgb.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32]
+        L.orc_tsdf_gather_color.argtypes = [vp, i32, i64, vp]
+        L.orc_tsdf_gather_color.restype = i64
+        L.orc_tsdf_scatter_color.argtypes = [vp, i32, i64, vp, vp]
+        L.orc_mc2.argtypes = [vp, i32, C.c_float, i64, vp, vp, vp]
+        L.orc_mc2.restype = i64
         L.orc_tsdf_query_points.argtypes = [vp, i32, i64, vp, vp]
         L.orc_tsdf_query_near.argtypes = [vp, i32, i64, vp, i32, vp]
         L.orc_tsdf_raycast.argtypes = [vp, i32, i64, vp, vp, C.c_float, vp, vp, vp]
@@ -145,6 +153,41 @@ class OracleTSDF:
         xyz = _f32(xyz)
         R, T = _f32(R), _f32(T)
         lib().orc_tsdf_integrate_points(self.h, _p(xyz), xyz.shape[0], _p(R), _p(T), submap, int(commit))
+
+    def set_color(self, enabled=True, same_proj=True, Kcolor=None):
+        """texture_enabled / color_same_proj / set_color_camera_intrinsic (dense_tsdf.py:13-16, mapping_common.py:28-29)."""
+        K = Kcolor if Kcolor is not None else [1, 0, 0, 0, 1, 0, 0, 0, 1]
+        lib().orc_tsdf_set_color(self.h, int(enabled), int(same_proj), K[0], K[4], K[2], K[5])
+
+    def integrate_depth_tex(self, R, T, depth, texture, submap=0, commit=True):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        texture = np.ascontiguousarray(texture, dtype=np.uint8)
+        R, T = _f32(R), _f32(T)
+        lib().orc_tsdf_integrate_depth_tex(self.h, _p(depth), _p(texture), texture.shape[0], texture.shape[1], depth.shape[0],
+                                           depth.shape[1], _p(R), _p(T), submap, int(commit))
+
+    def integrate_points_rgb(self, R, T, xyz, rgb, submap=0, commit=True):
+        xyz = _f32(xyz)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        R, T = _f32(R), _f32(T)
+        lib().orc_tsdf_integrate_points_rgb(self.h, _p(xyz), _p(rgb), xyz.shape[0], _p(R), _p(T), submap, int(commit))
+
+    def gather_color(self, submap=0):
+        n = self.count_active(submap)
+        c = np.zeros((n, 3), np.float32)
+        lib().orc_tsdf_gather_color(self.h, submap, n, _p(c))
+        return c
+
+    def scatter_color(self, submap, idx, col):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        col = _f32(col)
+        lib().orc_tsdf_scatter_color(self.h, submap, idx.shape[0], _p(idx), _p(col))
+
+    def marching_cubes_color(self, step=1, thres=0.1, cap_tri=1 << 21):
+        v = np.zeros((cap_tri * 3, 3), np.float32); nrm = np.zeros((cap_tri * 3, 3), np.float32); col = np.zeros((cap_tri * 3, 3), np.float32)
+        n = int(lib().orc_mc2(self.h, step, thres, cap_tri, _p(v), _p(nrm), _p(col)))
+        k = min(n, cap_tri)
+        return n, v[:3 * k], nrm[:3 * k], col[:3 * k]
 
     def commit(self):
         lib().orc_tsdf_commit(self.h)

@@ -100,6 +100,8 @@ struct Block {
   int occ[OB3];           // i8 in the reference (dense_tsdf.py:95); wider here, saturated on export
   float esdf[OB3];
   uint8_t eobs[OB3];
+  uint64_t cword[OB3];    // texture: winning (frame seq | closeness | rgb10) word per voxel (see color_word)
+  float col[OB3][3];      // texture: committed colour
   bool pending;           // has non-zero accumulators (listed in Tsdf::dirty)
   Block() { memset(this, 0, sizeof(*this)); }
 };
@@ -143,6 +145,11 @@ struct Tsdf {
   std::unordered_map<int, Pose> submap_pose;
   Stats st{};
   float colormap[1024][3];
+  // texture path (dense_tsdf.py:75-77,96-103): colour intrinsics, projection mode, frame sequence number
+  bool tex_enabled = false;
+  bool color_same_proj = true;
+  float fxc = 1, fyc = 1, cxc = 0, cyc = 0;
+  uint32_t frame_seq = 0;
 
   ~Tsdf() {
     for (auto& kv : blocks) delete kv.second;
@@ -225,9 +232,10 @@ struct Bucket {
   int count = 0;
   int64_t fx = 0, fy = 0, fz = 0, fd = 0;  // canonical exact sums
   float sx = 0, sy = 0, sz = 0, sd = 0;    // literal float sums (f32 or f16-rounded)
+  int64_t cr = 0, cg = 0, cb = 0;          // new_pcl_sum_color (dense_tsdf.py:76,234): exact integer channel sums
 };
 struct BucketGrid {
-  struct Raw { std::array<int, 3> key; float p[3]; float z; };
+  struct Raw { std::array<int, 3> key; float p[3]; float z; int rgb[3]; };
   std::vector<Raw> raw;
   std::vector<std::pair<std::array<int, 3>, Bucket>> cells;
   void finalize(int mode) {
@@ -240,6 +248,7 @@ struct BucketGrid {
       if (cells.empty() || cells.back().first != r.key) cells.emplace_back(r.key, Bucket());
       Bucket& q = cells.back().second;
       q.count += 1;
+      q.cr += r.rgb[0]; q.cg += r.rgb[1]; q.cb += r.rgb[2];
       if (mode == MODE_CANONICAL) {
         q.fx += llrintf(r.p[0] * (float)FIX);
         q.fy += llrintf(r.p[1] * (float)FIX);
@@ -263,9 +272,10 @@ struct BucketGrid {
 };
 
 // process_point  (dense_tsdf.py:227-234)
-static void bucket_add(const Tsdf& m, BucketGrid& g, const float p[3], float z) {
+static void bucket_add(const Tsdf& m, BucketGrid& g, const float p[3], float z, const int* rgb = nullptr) {
   const float vs = m.vs;
   BucketGrid::Raw r;
+  r.rgb[0] = rgb ? rgb[0] : 0; r.rgb[1] = rgb ? rgb[1] : 0; r.rgb[2] = rgb ? rgb[2] : 0;
   r.key = {iround(p[0] / vs), iround(p[1] / vs), iround(p[2] / vs)};  // xyz_to_ijk mapping_common.py:240-243
   r.p[0] = p[0]; r.p[1] = p[1]; r.p[2] = p[2];
   r.z = z;
@@ -276,6 +286,20 @@ static inline void rot(const float R[9], const float v[3], float o[3]) {  // inp
   o[0] = (R[0] * v[0] + R[1] * v[1]) + R[2] * v[2];
   o[1] = (R[3] * v[0] + R[4] * v[1]) + R[5] * v[2];
   o[2] = (R[6] * v[0] + R[7] * v[1]) + R[8] * v[2];
+}
+
+// Texture.  The reference overwrites color[xi] with the ray's mean colour at every sample (dense_tsdf.py:268-269):
+// racing rays, last writer wins.  Canonical rule: the winner is the sample with the largest word
+//   [ frame sequence number : 22 | closeness to the ray's surface point, 4095 - min(4095, |ds|/vs*16) : 12 | rgb 3x10 ]
+// i.e. later frames overwrite earlier ones (as in the reference) and, inside a frame, the sample nearest to its
+// surface point wins (then the larger packed colour).  Colours are the bucket mean / 255 quantised to 10 bits
+// (the reference stores f16: 11-bit significand).
+static inline uint64_t color_word(uint32_t seq, float ds, float vs, const Bucket& q) {
+  const float c = (float)q.count;
+  auto q10 = [&](int64_t sum) { float v = ((float)sum / c) / 255.0f; int k = (int)(v * 1023.0f + 0.5f); return (uint64_t)(k < 0 ? 0 : (k > 1023 ? 1023 : k)); };
+  int cl = (int)(fabsf(ds) / vs * 16.0f);
+  if (cl > 4095) cl = 4095;
+  return ((uint64_t)seq << 42) | ((uint64_t)(4095 - cl) << 30) | (q10(q.cr) << 20) | (q10(q.cg) << 10) | q10(q.cb);
 }
 
 // process_new_pcl  (dense_tsdf.py:236-270) - the ray-march hot loop.
@@ -344,6 +368,7 @@ static void raymarch(Tsdf& m, BucketGrid& g, const float Tin[3], int s) {
         if (!b->pending) { b->pending = true; m.dirty.push_back(b); }
         b->A[o] += (double)(w * ds);
         b->Bw[o] += (double)w;
+        if (m.tex_enabled) { const uint64_t cw = color_word(m.frame_seq, ds, vs, q); if (cw > b->cword[o]) b->cword[o] = cw; }  // :268-269
       } else if (mode == MODE_F32_LITERAL) {
         float T0 = b->T[o], W0 = b->W[o];
         b->T[o] = (T0 * W0 + w * ds) / (W0 + w);  // :264
@@ -374,6 +399,11 @@ static void commit(Tsdf& m, bool clamp) {
         b->obs[o] = 1;
         b->A[o] = 0.0f;
         b->Bw[o] = 0.0f;
+        if (m.tex_enabled && b->cword[o]) {
+          b->col[o][0] = (float)((b->cword[o] >> 20) & 1023) / 1023.0f;
+          b->col[o][1] = (float)((b->cword[o] >> 10) & 1023) / 1023.0f;
+          b->col[o][2] = (float)(b->cword[o] & 1023) / 1023.0f;
+        }
       }
     }
   }
@@ -453,8 +483,20 @@ void orc_tsdf_clear_stats(void* h) { ((Tsdf*)h)->st = Stats{}; }
 // recast_depth_to_map_kernel  (dense_tsdf.py:188-214) with unproject_point_dep
 // (mapping_common.py:31-41).  R9/T3 = input_R/input_T AFTER set_pose's
 // convert_by_base + f32 cast (mapping_common.py:149-156) - host plumbing is the caller's.
+void orc_tsdf_integrate_depth_tex(void* h, const uint16_t* depth, const uint8_t* tex, int TH, int TW, int H, int Wd, const float* R9,
+                                  const float* T3, int submap, int do_commit);
 void orc_tsdf_integrate_depth(void* h, const uint16_t* depth, int H, int Wd, const float* R9, const float* T3, int submap, int do_commit) {
+  orc_tsdf_integrate_depth_tex(h, depth, nullptr, 0, 0, H, Wd, R9, T3, submap, do_commit);
+}
+void orc_tsdf_set_color(void* h, int enabled, int same_proj, double fx, double fy, double cx, double cy) {
   Tsdf* m = (Tsdf*)h;
+  m->tex_enabled = enabled != 0; m->color_same_proj = same_proj != 0;
+  m->fxc = (float)fx; m->fyc = (float)fy; m->cxc = (float)cx; m->cyc = (float)cy;
+}
+void orc_tsdf_integrate_depth_tex(void* h, const uint16_t* depth, const uint8_t* tex, int TH, int TW, int H, int Wd, const float* R9,
+                                  const float* T3, int submap, int do_commit) {
+  Tsdf* m = (Tsdf*)h;
+  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;
   BucketGrid g;
   const int step = m->c.recast_step;
   const int hh = (int)((double)H / step), ww = (int)((double)Wd / step);  // range(0, h/step): float bound truncated
@@ -473,7 +515,19 @@ void orc_tsdf_integrate_depth(void* h, const uint16_t* depth, int H, int Wd, con
       float pt[3] = {((float)i - cx) * dep / fx, ((float)j - cy) * dep / fy, dep};  // mapping_common.py:37-40
       float p[3];
       rot(R9, pt, p);                                        // :203 (rotation only)
-      bucket_add(*m, g, p, dep);                             // :213 process_point(pt_map, dep)
+      int rgb[3] = {0, 0, 0};
+      if (m->tex_enabled && tex) {
+        int tj = j, ti = i;                                  // :206 color_same_proj: texture[j, i]
+        if (!m->color_same_proj) {                           // :209 color_ind_from_depth_pt (mapping_common.py:43-58)
+          ti = (int)((((float)i - cx) / fx) * m->fxc + m->cxc);
+          tj = (int)((((float)j - cy) / fy) * m->fyc + m->cyc);
+          // the reference tests color_i against h and color_j against w (swapped, :56); indices that pass that test
+          // but fall outside the texture are an out-of-bounds read there - canonical: pixel (0,0) as well
+          if (ti < 0 || ti >= TH || tj < 0 || tj >= TW || tj >= TH || ti >= TW) { ti = 0; tj = 0; }
+        }
+        if (tj < TH && ti < TW) { const uint8_t* px = tex + ((size_t)tj * TW + ti) * 3; rgb[0] = px[0]; rgb[1] = px[1]; rgb[2] = px[2]; }
+      }
+      bucket_add(*m, g, p, dep, rgb);                        // :207/:211/:213 process_point(pt_map, dep[, color])
     }
   }
   raymarch(*m, g, T3, submap);                               // :214
@@ -481,8 +535,15 @@ void orc_tsdf_integrate_depth(void* h, const uint16_t* depth, int H, int Wd, con
 }
 
 // recast_pcl_to_map_kernel  (dense_tsdf.py:167-186)
+void orc_tsdf_integrate_points_rgb(void* h, const float* xyz, const uint8_t* rgb, int n, const float* R9, const float* T3, int submap,
+                                   int do_commit);
 void orc_tsdf_integrate_points(void* h, const float* xyz, int n, const float* R9, const float* T3, int submap, int do_commit) {
+  orc_tsdf_integrate_points_rgb(h, xyz, nullptr, n, R9, T3, submap, do_commit);
+}
+void orc_tsdf_integrate_points_rgb(void* h, const float* xyz, const uint8_t* rgbs, int n, const float* R9, const float* T3, int submap,
+                                   int do_commit) {
   Tsdf* m = (Tsdf*)h;
+  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;
   BucketGrid g;
   const float maxr = (float)m->c.max_ray_length;
   for (int idx = 0; idx < n; idx++) {
@@ -493,7 +554,9 @@ void orc_tsdf_integrate_points(void* h, const float* xyz, int n, const float* R9
     float len = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);  // :176
     if (len < maxr) {                                        // :177
       m->st.n_valid++;
-      bucket_add(*m, g, p, len);                             // :185 process_point(pt, pt.norm())
+      int rgb[3] = {0, 0, 0};
+      if (m->tex_enabled && rgbs) { rgb[0] = rgbs[3 * idx]; rgb[1] = rgbs[3 * idx + 1]; rgb[2] = rgbs[3 * idx + 2]; }  // :179-183
+      bucket_add(*m, g, p, len, rgb);                        // :183/:185 process_point(pt, pt.norm()[, rgb])
     }
   }
   raymarch(*m, g, T3, submap);
@@ -544,6 +607,40 @@ int64_t orc_tsdf_gather(void* h, int submap, int64_t cap, int32_t* idx, float* t
   return n;
 }
 
+// colours of the observed voxels, same row order as orc_tsdf_gather (to_numpy data_color, dense_tsdf.py:437-440)
+int64_t orc_tsdf_gather_color(void* h, int submap, int64_t cap, float* col3) {
+  Tsdf* m = (Tsdf*)h;
+  struct Row { int i, j, k; float c[3]; };
+  std::vector<Row> rows;
+  for (auto& kv : m->blocks) {
+    if (kv.first.s != submap) continue;
+    Block* b = kv.second;
+    for (int o = 0; o < OB3; o++)
+      if (b->obs[o] > 0) rows.push_back({kv.first.x * OB + o / (OB * OB), kv.first.y * OB + (o / OB) % OB, kv.first.z * OB + o % OB,
+                                         {b->col[o][0], b->col[o][1], b->col[o][2]}});
+  }
+  std::sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+    if (a.i != b.i) return a.i < b.i;
+    if (a.j != b.j) return a.j < b.j;
+    return a.k < b.k;
+  });
+  int64_t n = 0;
+  for (auto& r : rows) {
+    if (n < cap) { col3[3 * n] = r.c[0]; col3[3 * n + 1] = r.c[1]; col3[3 * n + 2] = r.c[2]; }
+    n++;
+  }
+  return n;
+}
+void orc_tsdf_scatter_color(void* h, int submap, int64_t n, const int32_t* idx, const float* col3) {  // load_numpy :450-453
+  Tsdf* m = (Tsdf*)h;
+  for (int64_t r = 0; r < n; r++) {
+    int i = idx[3 * r], j = idx[3 * r + 1], k = idx[3 * r + 2];
+    if (!m->in_bounds(i, j, k)) continue;
+    int o; Block* b = m->touch(submap, i, j, k, &o);
+    b->col[o][0] = col3[3 * r]; b->col[o][1] = col3[3 * r + 1]; b->col[o][2] = col3[3 * r + 2];
+  }
+}
+
 // load_numpy  (dense_tsdf.py:442-454)
 void orc_tsdf_scatter(void* h, int submap, int64_t n, const int32_t* idx, const float* tsdf, const float* wts, const int32_t* occ) {
   Tsdf* m = (Tsdf*)h;
@@ -588,6 +685,8 @@ void orc_tsdf_fuse(void* hdst, void* hsrc) {
             int oo; Block* db = D->touch(0, c[0], c[1], c[2], &oo);
             float w_new = w + db->W[oo];                                    // :274
             db->T[oo] = (db->W[oo] * db->T[oo] + w * sb->T[o]) / w_new;    // :275
+            if (D->tex_enabled)                                             // :276-277
+              for (int ch = 0; ch < 3; ch++) db->col[oo][ch] = (db->W[oo] * db->col[oo][ch] + w * sb->col[o][ch]) / w_new;
             db->W[oo] = w_new;                                              // :278 (no Wmax clamp)
             db->obs[oo] = 1;                                                // :279
             db->occ[oo] = db->occ[oo] + sb->occ[o];                         // :280
@@ -622,7 +721,8 @@ int64_t orc_tsdf_surface(void* h, int submap, int64_t cap, float* xyz, float* rg
       if (n < cap) {
         xyz[3 * n] = p[0]; xyz[3 * n + 1] = p[1]; xyz[3 * n + 2] = p[2];
         int ci = (int)fmaxf(fminf(((p[2] - fl) / (ce - fl)) * 1023.0f, 1023.0f), 0.0f);  // mapping_common.py:216-219
-        rgb[3 * n] = m->colormap[ci][0]; rgb[3 * n + 1] = m->colormap[ci][1]; rgb[3 * n + 2] = m->colormap[ci][2];
+        if (m->tex_enabled) { rgb[3 * n] = b->col[o][0]; rgb[3 * n + 1] = b->col[o][1]; rgb[3 * n + 2] = b->col[o][2]; }  // :360-362
+        else { rgb[3 * n] = m->colormap[ci][0]; rgb[3 * n + 1] = m->colormap[ci][1]; rgb[3 * n + 2] = m->colormap[ci][2]; }
       }
       n++;
     }
@@ -661,7 +761,12 @@ int64_t orc_tsdf_slice(void* h, int submap, float z, float dz, int64_t cap, floa
 // generate_mesh_kernel / marching_on_a_cube / add_triangle / generate_normal
 // (marching_cube_mesher.py:84-187).  Triangles emitted in lexicographic
 // (block, cell, t) order; returns the true triangle demand.
+int64_t orc_mc2(void* h, int step, float thres, int64_t cap_tri, float* verts, float* normals, float* colors);
 int64_t orc_mc(void* h, int step, float thres, int64_t cap_tri, float* verts, float* normals) {
+  return orc_mc2(h, step, thres, cap_tri, verts, normals, nullptr);
+}
+// colors (optional, textured maps): vertexInterp_color + add_triangle_color (marching_cube_mesher.py:62-82, :104-108)
+int64_t orc_mc2(void* h, int step, float thres, int64_t cap_tri, float* verts, float* normals, float* colors) {
   Tsdf* m = (Tsdf*)h;
   const float vs = m->vs;
   const float EPS = 1e-6f;  // :6
@@ -688,6 +793,7 @@ int64_t orc_mc(void* h, int step, float thres, int64_t cap_tri, float* verts, fl
       int mask = mc_edge_mask(cube);  // :146
       if (mask == 0) continue;
       float vl[12][3];
+      float vc[12][3];
       for (int e = 0; e < 12; e++) {  // :151-172
         if (!(mask & (1 << e))) continue;
         int a = EDGE[e][0], bb = EDGE[e][1];
@@ -703,6 +809,20 @@ int64_t orc_mc(void* h, int step, float thres, int64_t cap_tri, float* verts, fl
           vl[e][1] = p1[1] + mu * (p2[1] - p1[1]);
           vl[e][2] = p1[2] + mu * (p2[2] - p1[2]);
         }
+        if (colors) {  // vertexInterp_color :62-82 (mu stays 0 in the two snap branches; the "is zero" tests only look at channel 0)
+          float mu = 0.0f;
+          if (!(fabsf(0.0f - v1) < EPS) && !(fabsf(0.0f - v2) < EPS)) mu = (0.0f - v1) / (v2 - v1);
+          float c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+          int oo; Block* cb;
+          if ((cb = m->find(s, i + GRID[a][0] * step, j + GRID[a][1] * step, k + GRID[a][2] * step, &oo))) for (int ch = 0; ch < 3; ch++) c1[ch] = cb->col[oo][ch];
+          if ((cb = m->find(s, i + GRID[bb][0] * step, j + GRID[bb][1] * step, k + GRID[bb][2] * step, &oo))) for (int ch = 0; ch < 3; ch++) c2[ch] = cb->col[oo][ch];
+          for (int ch = 0; ch < 3; ch++) {
+            float pc = c1[ch];
+            if (c1[0] == 0.0f) pc = c2[ch];
+            else if (!(c2[0] == 0.0f)) pc = c1[ch] + mu * (c2[ch] - c1[ch]);
+            vc[e][ch] = pc;
+          }
+        }
       }
       for (int t = 0; t < 5; t++) {  // :173-174 / :110-125
         int e0 = mc_tri(cube, 3 * t);
@@ -713,6 +833,7 @@ int64_t orc_mc(void* h, int step, float thres, int64_t cap_tri, float* verts, fl
             const float* p = vl[es[q]];
             float* vo = verts + (ntri * 3 + q) * 3;
             vo[0] = p[0] * vs; vo[1] = p[1] * vs; vo[2] = p[2] * vs;  // ijk_to_xyz :40-42
+            if (colors) { float* co = colors + (ntri * 3 + q) * 3; co[0] = vc[es[q]][0]; co[1] = vc[es[q]][1]; co[2] = vc[es[q]][2]; }
             float* no = normals + (ntri * 3 + q) * 3;
             if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) {
               // NaN TSDF corner (the shipped fixtures contain some) -> NaN vertex; round(NaN) is undefined in the

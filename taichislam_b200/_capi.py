@@ -16,7 +16,7 @@ E_INVALID, E_CUDA, E_POOL_FULL, E_CAPACITY, E_NOGPU = -1, -2, -3, -4, -5
 MEM_DEVICE, MEM_HOST = 0, 1
 F_COMMIT = 1
 MAX_BATCH = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class TslamError(RuntimeError):
@@ -33,7 +33,7 @@ class TsdfConfig(C.Structure):
                 ("is_global_map", C.c_int32),
                 ("disp_floor", C.c_double), ("disp_ceiling", C.c_double),
                 ("max_submaps", C.c_int32), ("max_blocks", C.c_int32),
-                ("max_image_pixels", C.c_int32), ("max_points", C.c_int32)]
+                ("max_image_pixels", C.c_int32), ("max_points", C.c_int32), ("texture_enabled", C.c_int32)]
 
 
 class OctoConfig(C.Structure):
@@ -61,6 +61,13 @@ SIGNATURES = {
     "tslam_tsdf_integrate_depth": (C.c_int, [_vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp]),
     "tslam_tsdf_queue_depth": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "tslam_tsdf_flush": (C.c_int, [_vp, _vp]),
+    "tslam_tsdf_set_color_intrinsics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "tslam_tsdf_integrate_depth_tex": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp]),
+    "tslam_tsdf_queue_depth_tex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "tslam_tsdf_integrate_points_rgb": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32, _vp, _vp, _i32, C.c_int, _vp]),
+    "tslam_tsdf_gather2": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "tslam_tsdf_scatter2": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tslam_mc_generate2": (C.c_int, [_vp, _i32, _f32, _i64, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "tslam_tsdf_integrate_points": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _i32, C.c_int, _vp]),
     "tslam_tsdf_commit": (C.c_int, [_vp, _vp]),
     "tslam_tsdf_count_active": (C.c_int, [_vp, _i32, C.POINTER(_i64)]),

@@ -44,6 +44,8 @@ struct TsGrid {
   float2* tw;                 // [max_blocks*4096]
   uint8_t* obs;               // [max_blocks*4096]
   int8_t* occ;                // [max_blocks*4096]
+  unsigned long long* cword;  // [max_blocks*4096] texture: winning colour word per voxel (null unless texture_enabled)
+  float4* col;                // [max_blocks*4096] texture: committed colour rgb (+pad)
   uint8_t* ghost;             // [max_blocks] 1 = halo copy of a block owned by another rank (multi-GPU tiling)
   float* esdf;                // [max_blocks*4096] (allocated lazily by the ESDF path)
   int* dirty_flag;            // [max_blocks]
@@ -165,9 +167,10 @@ struct TsFrame {
   float R[9];
   float T[3];
   int submap;
+  unsigned int seq;  // frame sequence number of the map (texture: later frames overwrite earlier colours)
 };
 struct TsBatch {
-  TsFrame f[TSLAM_MAX_BATCH];  // 64 * 52 B = 3328 B
+  TsFrame f[TSLAM_MAX_BATCH];  // 64 * 56 B = 3584 B
 };
 
 struct TsIntrin {
@@ -179,6 +182,10 @@ struct TsIntrin {
   float max_ray;           // f32(max_ray_length)
   int internal_voxels;
   int step;
+  // texture (dense_tsdf.py:204-211, mapping_common.py:43-58)
+  float fxc, fyc, cxc, cyc;
+  int tex;         // texture_enabled
+  int same_proj;   // color_same_proj
 };
 
 // per-frame bucket entry (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z),
@@ -187,7 +194,8 @@ struct __align__(64) TsBucket {
   unsigned long long key;  // packed (bx,by,bz)+1, 0 = empty
   long long sx, sy, sz, sd;
   int cnt;
-  int pad[5];
+  unsigned int cr, cg, cb;  // new_pcl_sum_color: exact integer channel sums
+  int pad[2];
 };
 
 struct TsCounters {  // device-side statistics (tslam_tsdf_get_stats)
@@ -208,6 +216,10 @@ struct tslam_tsdf {
   uint32_t ray_list_cap;
   int* n_rays;         // device counter
   uint16_t* depth_stage;  // device staging for host depth input [TSLAM_MAX_BATCH * max_image_pixels]
+  uint8_t* tex_stage;     // device staging for host textures [2 * TSLAM_MAX_BATCH * max_image_pixels * 3] (texture_enabled only)
+  uint8_t* rgb_stage;     // device staging for point-cloud colours
+  unsigned int frame_seq; // frames integrated so far (saturates at 2^22-1)
+  int q_th, q_tw, q_has_tex;
   float* points_stage;    // device staging for host point clouds
   TsCounters* counters;
   float* pose_R;       // device pose table [max_submaps*9]

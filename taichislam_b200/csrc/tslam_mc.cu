@@ -176,9 +176,33 @@ __global__ void __launch_bounds__(1024) k_mc_scan(const int* n_blocks_p, int max
   if (threadIdx.x == 0) *total = carry;
 }
 
+// vertexInterp_color (marching_cube_mesher.py:62-82) for the vertex on edge e of the cell at (i,j,k).  Reference
+// quirks kept: mu stays 0 in the two snap branches (:66-71), and the "colour is zero" tests look at channel 0 only.
+__device__ __forceinline__ float4 mc_read_col(const TsGrid& g, int s, int i, int j, int k) {
+  const int blk = ts_find(g, ts_pack_key(s, i >> TS_BSHIFT, j >> TS_BSHIFT, k >> TS_BSHIFT));
+  if (blk < 0 || !g.col) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return g.col[(size_t)blk * TS_B3 + ts_voxel_off(i, j, k)];
+}
+__device__ __forceinline__ void mc_vertex_color(const TsGrid& g, int s, int i, int j, int k, int step, int e, const float* val, float* out) {
+  int a, bb, ax, ay, az, cx, cy, cz;
+  mc_edge_ends(e, a, bb);
+  mc_corner(a, ax, ay, az);
+  mc_corner(bb, cx, cy, cz);
+  const float v1 = val[a], v2 = val[bb];
+  float mu = 0.0f;
+  if (!(fabsf(0.0f - v1) < MC_EPS) && !(fabsf(0.0f - v2) < MC_EPS)) mu = (0.0f - v1) / (v2 - v1);
+  const float4 c1 = mc_read_col(g, s, i + ax * step, j + ay * step, k + az * step);
+  const float4 c2 = mc_read_col(g, s, i + cx * step, j + cy * step, k + cz * step);
+  if (c1.x == 0.0f) { out[0] = c2.x; out[1] = c2.y; out[2] = c2.z; }
+  else if (!(c2.x == 0.0f)) {
+    out[0] = c1.x + mu * (c2.x - c1.x); out[1] = c1.y + mu * (c2.y - c1.y); out[2] = c1.z + mu * (c2.z - c1.z);
+  } else { out[0] = c1.x; out[1] = c1.y; out[2] = c1.z; }
+}
+
 // pass 2: emit.  vertexInterp (:44-60), add_triangle (:95-102), generate_normal (:84-93).
 __global__ void __launch_bounds__(256) k_mc_emit(TsGrid g, float thres, float vs, const unsigned int* blk_tris,
-                                                  const unsigned long long* blk_off, long long cap_tri, float* verts, float* normals) {
+                                                  const unsigned long long* blk_off, long long cap_tri, float* verts, float* normals,
+                                                  float* colors) {
   __shared__ McTile tile;
   __shared__ unsigned int warp_sum[8];
   __shared__ unsigned int run_base;
@@ -249,6 +273,7 @@ __global__ void __launch_bounds__(256) k_mc_emit(TsGrid g, float thres, float vs
             const float px = vl[e][0], py = vl[e][1], pz = vl[e][2];
             float* vo = verts + ((size_t)tri * 3 + q) * 3;
             vo[0] = px * vs; vo[1] = py * vs; vo[2] = pz * vs;  // ijk_to_xyz :40-42 (map-local metres)
+            if (colors) mc_vertex_color(g, s, i, j, k, 1, e, val, colors + ((size_t)tri * 3 + q) * 3);  // :104-108
             // generate_normal :84-93 - central differences at round(vertex), from the staged tile
             float* no = normals + ((size_t)tri * 3 + q) * 3;
             if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {  // NaN TSDF corner: round(NaN) is undefined (:86)
@@ -278,7 +303,7 @@ __device__ __forceinline__ void mc_read(const TsGrid& g, int s, int i, int j, in
 }
 
 __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float thres, float vs, long long cap_tri, float* verts,
-                                                     float* normals, unsigned long long* counter) {
+                                                     float* normals, float* colors, unsigned long long* counter) {
   const int nb = min(*g.n_blocks, g.max_blocks);
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
@@ -331,6 +356,7 @@ __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float th
           const float px = vl[e][0], py = vl[e][1], pz = vl[e][2];
           float* vo = verts + ((size_t)tri * 3 + q) * 3;
           vo[0] = px * vs; vo[1] = py * vs; vo[2] = pz * vs;
+          if (colors) mc_vertex_color(g, s, i, j, k, step, e, val, colors + ((size_t)tri * 3 + q) * 3);
           float* no = normals + ((size_t)tri * 3 + q) * 3;
           if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
             no[0] = no[1] = no[2] = __int_as_float(0x7fc00000);
@@ -355,6 +381,10 @@ __global__ void __launch_bounds__(256) k_mc_generic(TsGrid g, int step, float th
 
 extern "C" int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float thres, int64_t cap_tri, float* verts, float* normals,
                                  int64_t* n_tri_out, void* stream) {
+  return tslam_mc_generate2(m, step, thres, cap_tri, verts, normals, nullptr, n_tri_out, stream);
+}
+extern "C" int tslam_mc_generate2(tslam_tsdf_t* m, int32_t step, float thres, int64_t cap_tri, float* verts, float* normals,
+                                  float* colors, int64_t* n_tri_out, void* stream) {
   if (!m || !verts || !normals || !n_tri_out || step < 1 || cap_tri < 0) return TSLAM_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = mc_upload_tables();
@@ -371,13 +401,13 @@ extern "C" int tslam_mc_generate(tslam_tsdf_t* m, int32_t step, float thres, int
     TS_LAUNCH_CHECK(m);
     k_mc_scan<<<1, 1024, 0, st>>>(m->g.n_blocks, m->g.max_blocks, blk_tris, blk_off, d_total);
     TS_LAUNCH_CHECK(m);
-    k_mc_emit<<<m->sm_count * 4, 256, 0, st>>>(m->g, thres, m->in.vs, blk_tris, blk_off, cap_tri, verts, normals);
+    k_mc_emit<<<m->sm_count * 4, 256, 0, st>>>(m->g, thres, m->in.vs, blk_tris, blk_off, cap_tri, verts, normals, colors);
     TS_LAUNCH_CHECK(m);
     TS_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
     TS_CUDA(cudaStreamSynchronize(st));
   } else {
     TS_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
-    k_mc_generic<<<m->sm_count * 8, 256, 0, st>>>(m->g, step, thres, m->in.vs, cap_tri, verts, normals, d_total);
+    k_mc_generic<<<m->sm_count * 8, 256, 0, st>>>(m->g, step, thres, m->in.vs, cap_tri, verts, normals, colors, d_total);
     TS_LAUNCH_CHECK(m);
     TS_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
     TS_CUDA(cudaStreamSynchronize(st));

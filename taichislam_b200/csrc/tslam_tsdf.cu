@@ -83,7 +83,7 @@ __device__ __forceinline__ void red_add_u32(unsigned int* addr, unsigned int v) 
 // lanes; `valid` masks lanes without a point.  Returns the table slot when this lane OPENED a bucket
 // (the bucket becomes one ray; the caller appends it to the ray list), else -1.
 __device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, float px, float py, float pz, float dep,
-                                                 float vs, bool agg_ok, int* err) {
+                                                 float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   if (!valid) return -1;
   const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
@@ -99,6 +99,11 @@ __device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint
       qy = (long long)__reduce_add_sync(grp, (int)qy);
       qz = (long long)__reduce_add_sync(grp, (int)qz);
       qd = (long long)__reduce_add_sync(grp, (int)qd);
+      if (tex) {
+        cr = __reduce_add_sync(grp, cr);
+        cg = __reduce_add_sync(grp, cg);
+        cb = __reduce_add_sync(grp, cb);
+      }
     }
     if (!leader) return -1;
   }
@@ -126,6 +131,11 @@ __device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint
   red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
   red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
   red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
+  if (tex) {  // new_pcl_sum_color += rgb (dense_tsdf.py:233-234), exact integer sums
+    red_add_u32(&b->cr, (unsigned int)cr);
+    red_add_u32(&b->cg, (unsigned int)cg);
+    red_add_u32(&b->cb, (unsigned int)cb);
+  }
   return fresh;
 }
 
@@ -162,13 +172,15 @@ __device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_bas
 __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int frame_stride, int row_mul, int w, int hh, int ww,
                                                        const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
                                                        TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
-                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
+                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err,
+                                                       const uint8_t* __restrict__ tex, int th, int tw) {
   const int f = blockIdx.z;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ii = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
   const int jj = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
   bool valid = false;
   float px = 0.f, py = 0.f, pz = 0.f, dep = 0.f;
+  int cr = 0, cg = 0, cb = 0;
   if (ii < ww && jj < hh) {
     const int j = jj * in.step, i = ii * in.step;
     // row_mul = recast_step for full frames, 1 when the staging copy already dropped the unsampled rows
@@ -183,10 +195,25 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
       px = (fr.R[0] * x + fr.R[1] * y) + fr.R[2] * dep;     // :203 input_R @ pt (rotation only)
       py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * dep;
       pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * dep;
+      if (tex) {
+        int tj = j, ti = i;  // color_same_proj: texture[j, i] (:206)
+        if (!in.same_proj) {  // color_ind_from_depth_pt (mapping_common.py:43-58, called at :209)
+          ti = (int)((((float)i - in.cx) / in.fx) * in.fxc + in.cxc);
+          tj = (int)((((float)j - in.cy) / in.fy) * in.fyc + in.cyc);
+          // the reference tests color_i against h and color_j against w (swapped, :56); what passes that test but lies
+          // outside the image is an out-of-bounds read there - here pixel (0,0) too
+          if (ti < 0 || ti >= th || tj < 0 || tj >= tw || tj >= th || ti >= tw) { ti = 0; tj = 0; }
+        }
+        if (tj < th && ti < tw) {
+          const uint8_t* p = tex + ((size_t)f * th * tw + (size_t)tj * tw + ti) * 3;
+          cr = p[0]; cg = p[1]; cb = p[2];
+        }
+      }
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err);
+  const int fresh = bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err,
+                                      tex != nullptr, cr, cg, cb);
   append_rays_cta(fresh, (uint32_t)f * bucket_cap, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
 }
@@ -195,8 +222,9 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
 __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
                                                         TsIntrin in, int agg_ok, TsBucket* buckets, uint32_t bucket_cap,
                                                         uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
-                                                        int* err) {
+                                                        int* err, const uint8_t* __restrict__ rgb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int cr = 0, cg = 0, cb = 0;
   bool valid = false;
   float px = 0.f, py = 0.f, pz = 0.f, len = 0.f;
   if (t < n) {
@@ -207,9 +235,10 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
     pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * z;
     len = sqrtf((px * px + py * py) + pz * pz);       // :176
     valid = len < in.max_ray;                          // :177
+    if (rgb) { cr = rgb[3 * (size_t)t]; cg = rgb[3 * (size_t)t + 1]; cb = rgb[3 * (size_t)t + 2]; }  // :179-182
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err);  // :185
+  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err, rgb != nullptr, cr, cg, cb);  // :183/:185
   append_rays_cta(fresh, 0u, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
@@ -237,6 +266,7 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
 #define RM_FIX 16777216.0f   // 2^24
 #define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
 #define RM_SMEM (RM_WIN3 * 16 + RM_TAB * 8)
+#define RM_SMEM_TEX (RM_SMEM + RM_WIN3 * 8)  // textured maps: + one 64-bit colour word per window voxel
 
 // block lookup for the march loop: shared-memory table first (global loads queue behind the reduction traffic in
 // the in-order L1TEX pipe: measured as the top stall), hash grid on a miss.
@@ -259,6 +289,7 @@ __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
   if (c) atomicAdd(hi, c);
 }
 
+template <bool TEX>
 __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
                                                               TsBucket* buckets, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
                                                               const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
@@ -268,6 +299,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   unsigned int* const w_blo = win + 2 * RM_WIN3;
   int* const w_bhi = (int*)(win + 3 * RM_WIN3);
   unsigned long long* const btab = (unsigned long long*)(win + 4 * RM_WIN3);
+  unsigned long long* const w_cw = btab + RM_TAB;  // TEX only: colour word of every window voxel
   __shared__ int s_org[4];   // window origin (voxels) and submap
   __shared__ int s_blk[8];   // the <= 8 blocks the window overlaps
 
@@ -278,6 +310,8 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   const float rvs = in.rvs;
   for (int e = threadIdx.x; e < 4 * RM_WIN3; e += RM_THREADS) win[e] = 0u;
   for (int e = threadIdx.x; e < RM_TAB; e += RM_THREADS) btab[e] = TS_EMPTY;
+  if (TEX)
+    for (int e = threadIdx.x; e < RM_WIN3; e += RM_THREADS) w_cw[e] = 0ull;
 
   // control flow is kept WARP-UNIFORM (32 consecutive rays per warp, march to the longest ray, predicated lanes)
   for (uint32_t base = blockIdx.x * RM_THREADS; base < n_rays; base += gridDim.x * RM_THREADS) {
@@ -294,6 +328,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
     bool live = r < n_rays;
     int cnt = 0, s = 0, n = 0;
     long long sx = 0, sy = 0, sz = 0, sd = 0;
+    unsigned int ccr = 0, ccg = 0, ccb = 0;
     uint32_t f = 0;
     if (live) {
       const uint32_t id = ray_list[r];
@@ -301,6 +336,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       TsBucket* bk = &buckets[id];
       cnt = bk->cnt;
       sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
+      if (TEX) { ccr = bk->cr; ccg = bk->cg; ccb = bk->cb; }
       // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       uint4* q = reinterpret_cast<uint4*>(bk);
@@ -340,6 +376,16 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       }
     }
     const bool win_ok = (s == ws) && wgt < 120.0f;  // fixed-point range of the window words
+    // textured maps: every sample also raises the voxel's colour word [frame seq : 22][closeness : 12][rgb : 30]
+    // (atomicMax; decoded by k_commit) - in the window's shared-memory copy for near-field samples
+    unsigned long long cw_hi = 0ull;
+    if (TEX && live && cnt > 0) {
+      const float c = (float)cnt;
+      const int qr = min(1023, (int)((((float)ccr / c) / 255.0f) * 1023.0f + 0.5f));  // sum_color/c/255 (:269), 10 bits
+      const int qg = min(1023, (int)((((float)ccg / c) / 255.0f) * 1023.0f + 0.5f));
+      const int qb = min(1023, (int)((((float)ccb / c) / 255.0f) * 1023.0f + 0.5f));
+      cw_hi = ((unsigned long long)batch.f[f].seq << 42) | ((unsigned long long)qr << 20) | ((unsigned long long)qg << 10) | (unsigned long long)qb;
+    }
     const int wq = __float2int_rn(wgt * RM_FIX);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
     float jf = 0.0f;
@@ -360,6 +406,10 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
         const int e = (int)((dx << 8) | (dy << 4) | dz);
         win_add(&w_alo[e], &w_ahi[e], __float2int_rn(a * RM_FIX));
         win_add(&w_blo[e], &w_bhi[e], wq);
+        if (TEX) {
+          const int cl = min(4095, (int)(fabsf(ds) / vs * 16.0f));
+          atomicMax(&w_cw[e], cw_hi | ((unsigned long long)(4095 - cl) << 30));
+        }
         my_updates++;
       }
       const bool far = inb && !in_win;
@@ -370,7 +420,12 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       }
       __syncwarp();
       if (far && cur_blk >= 0) {  // cur_blk < 0: pool exhausted (error flag raised)
-        red_add_f32x2(&g.acc[(size_t)cur_blk * TS_B3 + ts_voxel_off(xi, yi, zi)], a, wgt);  // :264,:267
+        const size_t vo = (size_t)cur_blk * TS_B3 + ts_voxel_off(xi, yi, zi);
+        red_add_f32x2(&g.acc[vo], a, wgt);  // :264,:267
+        if (TEX) {  // color[xi] = ray colour (:268-269): latest frame, then the sample closest to its surface point
+          const int cl = min(4095, (int)(fabsf(ds) / vs * 16.0f));
+          atomicMax(&g.cword[vo], cw_hi | ((unsigned long long)(4095 - cl) << 30));
+        }
         my_updates++;
       }
     }
@@ -419,6 +474,10 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       const float A = (float)(((double)ahi * 4294967296.0 + (double)alo) * (1.0 / 16777216.0));
       const float B = (float)(((double)bhi * 4294967296.0 + (double)blo) * (1.0 / 16777216.0));
       red_add_f32x2(&g.acc[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], A, B);
+      if (TEX) {
+        atomicMax(&g.cword[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], w_cw[e]);
+        w_cw[e] = 0ull;
+      }
     }
     __syncthreads();
   }
@@ -462,6 +521,17 @@ __global__ void __launch_bounds__(256) k_commit(TsGrid g, int clamp, int fused_o
         tw[v] = r;
         obs[v] = 1;
         acc[v] = make_float2(0.0f, 0.0f);
+        if (g.col) {
+          float4* col = g.col + (size_t)blk * TS_B3;
+          if (fused_obs) {  // fusion: col holds sum(w*c) (:277) -> weighted mean
+            float4 c = col[v];
+            c.x = c.x / wn; c.y = c.y / wn; c.z = c.z / wn;
+            col[v] = c;
+          } else {
+            const unsigned long long cw = g.cword[(size_t)blk * TS_B3 + v];
+            if (cw) col[v] = make_float4((float)((cw >> 20) & 1023) / 1023.0f, (float)((cw >> 10) & 1023) / 1023.0f, (float)(cw & 1023) / 1023.0f, 0.0f);
+          }
+        }
       }
     }
     if (threadIdx.x == 0) g.dirty_flag[blk] = 0;
@@ -621,6 +691,7 @@ static void ts_fill_intrin(tslam_tsdf* m) {
   m->in.max_ray = (float)c.max_ray_length;
   m->in.internal_voxels = c.internal_voxels;
   m->in.step = c.recast_step;
+  m->in.tex = c.texture_enabled;
 }
 
 extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** out) {
@@ -675,6 +746,14 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   TS_CUDA(cudaMemset(g.obs, 0, nv));
   TS_CUDA(cudaMemset(g.occ, 0, nv));
   g.esdf = nullptr;
+  g.cword = nullptr;
+  g.col = nullptr;
+  if (m->cfg.texture_enabled) {
+    TS_CUDA(cudaMalloc(&g.cword, nv * 8));
+    TS_CUDA(cudaMalloc(&g.col, nv * 16));
+    TS_CUDA(cudaMemset(g.cword, 0, nv * 8));
+    TS_CUDA(cudaMemset(g.col, 0, nv * 16));
+  }
   TS_CUDA(cudaMalloc(&g.ghost, (size_t)g.max_blocks));
   TS_CUDA(cudaMemset(g.ghost, 0, (size_t)g.max_blocks));
   TS_CUDA(cudaMalloc(&g.dirty_flag, (size_t)g.max_blocks * 4));
@@ -708,6 +787,10 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     TS_CUDA(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
   }
   TS_CUDA(cudaMalloc(&m->points_stage, (size_t)m->cfg.max_points * 12));
+  if (m->cfg.texture_enabled) {
+    TS_CUDA(cudaMalloc(&m->tex_stage, (size_t)2 * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 3));
+    TS_CUDA(cudaMalloc(&m->rgb_stage, (size_t)m->cfg.max_points * 3));
+  }
   TS_CUDA(cudaMalloc(&m->counters, sizeof(TsCounters)));
   TS_CUDA(cudaMemset(m->counters, 0, sizeof(TsCounters)));
   TS_CUDA(cudaMalloc(&m->pose_R, (size_t)m->cfg.max_submaps * 9 * 4));
@@ -718,7 +801,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   fill_jet_host(cm.data());
   TS_CUDA(cudaMalloc(&m->colormap, cm.size() * 4));
   TS_CUDA(cudaMemcpy(m->colormap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice));
-  TS_CUDA(cudaFuncSetAttribute(k_raymarch, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_raymarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_raymarch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_TEX));
   TS_CUDA(cudaFuncSetAttribute(k_commit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM));
   TS_CUDA(cudaDeviceSynchronize());
   *out = m;
@@ -733,6 +817,10 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (g.esdf) cudaFree(g.esdf);
   if (m->esdf_aux) cudaFree(m->esdf_aux);
   if (m->mc_scratch) cudaFree(m->mc_scratch);
+  if (g.cword) cudaFree(g.cword);
+  if (g.col) cudaFree(g.col);
+  if (m->tex_stage) cudaFree(m->tex_stage);
+  if (m->rgb_stage) cudaFree(m->rgb_stage);
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
@@ -763,6 +851,8 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
     if (g.esdf) TS_CUDA(cudaMemsetAsync(g.esdf, 0, nv * 4, st));
     TS_CUDA(cudaMemsetAsync(g.dirty_flag, 0, (size_t)nb * 4, st));
     TS_CUDA(cudaMemsetAsync(g.ghost, 0, (size_t)nb, st));
+    if (g.cword) TS_CUDA(cudaMemsetAsync(g.cword, 0, nv * 8, st));
+    if (g.col) TS_CUDA(cudaMemsetAsync(g.col, 0, nv * 16, st));
   }
   TS_CUDA(cudaMemsetAsync(m->scratch_i, 0, 4 * sizeof(int), st));  // n_blocks, n_dirty, err, n_rays
   return TSLAM_OK;
@@ -772,6 +862,13 @@ extern "C" int tslam_tsdf_set_intrinsics(tslam_tsdf_t* m, double fx, double fy, 
   if (!m) return TSLAM_E_INVALID;
   m->cfg.fx = fx; m->cfg.fy = fy; m->cfg.cx = cx; m->cfg.cy = cy;
   ts_fill_intrin(m);
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_set_color_intrinsics(tslam_tsdf_t* m, double fx, double fy, double cx, double cy, int color_same_proj) {
+  if (!m) return TSLAM_E_INVALID;
+  m->in.fxc = (float)fx; m->in.fyc = (float)fy; m->in.cxc = (float)cx; m->in.cyc = (float)cy;
+  m->in.same_proj = color_same_proj ? 1 : 0;
   return TSLAM_OK;
 }
 
@@ -789,7 +886,8 @@ static int ts_launch_commit(tslam_tsdf* m, cudaStream_t st, int clamp, int fused
   int grid = m->sm_count * 8;
   k_collect_dirty<<<(m->g.max_blocks + 255) / 256 < m->sm_count * 4 ? (m->g.max_blocks + 255) / 256 : m->sm_count * 4, 256, 0, st>>>(m->g);
   TS_LAUNCH_CHECK(m);
-  static const bool plain = getenv("TSLAM_COMMIT_PLAIN") != nullptr;  // A/B switch for the non-TMA variant
+  static const bool plain_env = getenv("TSLAM_COMMIT_PLAIN") != nullptr;  // A/B switch for the non-TMA variant
+  const bool plain = plain_env || m->g.col != nullptr;  // textured maps: the per-thread variant also folds the colours
   if (plain) k_commit<<<grid, 256, 0, st>>>(m->g, clamp, fused);
   else k_commit_tma<<<m->sm_count * 3, 256, CM_SMEM, st>>>(m->g, clamp, fused);
   TS_LAUNCH_CHECK(m);
@@ -830,22 +928,40 @@ extern "C" int tslam_tsdf_commit(tslam_tsdf_t* m, void* stream) {
   return ts_flush_pending(m, (cudaStream_t)stream);
 }
 
-static void ts_fill_frame(TsFrame& fr, const float* R9, const float* T3, int submap) {
+static void ts_fill_frame(tslam_tsdf* m, TsFrame& fr, const float* R9, const float* T3, int submap) {
   memcpy(fr.R, R9, 36);
   memcpy(fr.T, T3, 12);
   fr.submap = submap;
+  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;  // 1, 2, ... (texture: later frames win)
+  fr.seq = m->frame_seq;
 }
 
 static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
-                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted);
+                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted,
+                                   const uint8_t* tex = nullptr, int th = 0, int tw = 0);
 extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                           const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream) {
   return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0);
 }
+static int ts_check_tex(tslam_tsdf* m, const uint8_t* tex, int th, int tw) {
+  if (!tex) return TSLAM_OK;
+  if (!m->g.cword) { ts_set_error("colour image given but the map was created with texture_enabled=0"); return TSLAM_E_INVALID; }
+  if (th <= 0 || tw <= 0 || (long long)th * tw > m->cfg.max_image_pixels) { ts_set_error("texture %dx%d exceeds max_image_pixels=%d", th, tw, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
+  return TSLAM_OK;
+}
+extern "C" int tslam_tsdf_integrate_depth_tex(tslam_tsdf_t* m, const uint16_t* depth, const uint8_t* tex, int mem, int32_t n_frames, int32_t h,
+                                              int32_t w, int32_t th, int32_t tw, const float* R9s, const float* T3s,
+                                              const int32_t* submap_ids, int flags, void* stream) {
+  if (!m) return TSLAM_E_INVALID;
+  int rc = ts_check_tex(m, tex, th, tw);
+  if (rc) return rc;
+  return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0, tex, th, tw);
+}
 // rows_compacted: the frames hold only the sampled rows (hh = h/step rows of w pixels each) - the per-frame queue
 // stages them that way with a strided 2-D copy, halving the host->device bytes for recast_step 2.
 static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
-                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted) {
+                                   const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted,
+                                   const uint8_t* tex, int th, int tw) {
   if (!m || !depth || !R9s || !T3s || n_frames < 0 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
   if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -860,7 +976,7 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     for (int q = 0; q < nf; q++) {
       const int sid = submap_ids ? submap_ids[base + q] : 0;
       if (sid < 0 || sid >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", sid); return TSLAM_E_INVALID; }
-      ts_fill_frame(batch.f[q], R9s + 9 * (size_t)(base + q), T3s + 3 * (size_t)(base + q), sid);
+      ts_fill_frame(m, batch.f[q], R9s + 9 * (size_t)(base + q), T3s + 3 * (size_t)(base + q), sid);
     }
     const int rows_stored = rows_compacted ? hh : h;
     const uint16_t* src = depth + (size_t)base * rows_stored * w;
@@ -868,16 +984,25 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
       TS_CUDA(cudaMemcpyAsync(m->depth_stage, src, (size_t)nf * h * w * 2, cudaMemcpyHostToDevice, st));
       src = m->depth_stage;
     }
+    const uint8_t* tsrc = tex ? tex + (size_t)base * th * tw * 3 : nullptr;
+    if (tex && mem == TSLAM_MEM_HOST) {
+      TS_CUDA(cudaMemcpyAsync(m->tex_stage, tsrc, (size_t)nf * th * tw * 3, cudaMemcpyHostToDevice, st));
+      tsrc = m->tex_stage;
+    }
     cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
     dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
     const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
     k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
-                                          m->n_rays, m->ray_list_cap, m->counters, m->g.err);
+                                          m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-    k_raymarch<<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                             m->ray_list_cap, m->counters);
+    if (m->g.cword)
+      k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                     m->ray_list_cap, m->counters);
+    else
+      k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                      m->ray_list_cap, m->counters);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
     k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
@@ -894,17 +1019,27 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
 
 extern "C" int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, int mem, int32_t n, const float* R9, const float* T3,
                                            int32_t submap, int flags, void* stream) {
+  return tslam_tsdf_integrate_points_rgb(m, xyz, nullptr, mem, n, R9, T3, submap, flags, stream);
+}
+extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz, const uint8_t* rgb, int mem, int32_t n, const float* R9,
+                                               const float* T3, int32_t submap, int flags, void* stream) {
+  if (m && rgb && !m->g.cword) { ts_set_error("point colours given but the map was created with texture_enabled=0"); return TSLAM_E_INVALID; }
   if (!m || (!xyz && n > 0) || !R9 || !T3 || n < 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
   if (n > m->cfg.max_points) { ts_set_error("n=%d exceeds max_points=%d", n, m->cfg.max_points); return TSLAM_E_INVALID; }
   if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   TsBatch batch;
-  ts_fill_frame(batch.f[0], R9, T3, submap);
+  ts_fill_frame(m, batch.f[0], R9, T3, submap);
   const float* src = xyz;
   if (mem == TSLAM_MEM_HOST) {
     TS_CUDA(cudaMemcpyAsync(m->points_stage, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     src = m->points_stage;
+  }
+  const uint8_t* csrc = rgb;
+  if (rgb && mem == TSLAM_MEM_HOST) {
+    TS_CUDA(cudaMemcpyAsync(m->rgb_stage, rgb, (size_t)n * 3, cudaMemcpyHostToDevice, st));
+    csrc = m->rgb_stage;
   }
   const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
@@ -912,11 +1047,15 @@ extern "C" int tslam_tsdf_integrate_points(tslam_tsdf_t* m, const float* xyz, in
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
   const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
   k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
-                                                    m->ray_list_cap, m->counters, m->g.err);
+                                                    m->ray_list_cap, m->counters, m->g.err, csrc);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-  k_raymarch<<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                           m->ray_list_cap, m->counters);
+  if (m->g.cword)
+    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                   m->ray_list_cap, m->counters);
+  else
+    k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                    m->ray_list_cap, m->counters);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
   k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
@@ -945,7 +1084,9 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   const uint16_t* src = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels;
   m->q_n = 0;  // (integrate may recurse into flush through readers; the queue is empty from here on)
   m->q_buf = b ^ 1;
-  int rc = ts_integrate_depth_impl(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st, 0);
+  const uint8_t* tsrc = m->q_has_tex ? m->tex_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 3 : nullptr;
+  int rc = ts_integrate_depth_impl(m, src, TSLAM_MEM_DEVICE, n, m->q_h, m->q_w, m->q_R, m->q_T, m->q_s, TSLAM_F_COMMIT, (void*)st, 0,
+                                   tsrc, m->q_th, m->q_tw);
   if (rc) return rc;
   TS_CUDA(cudaEventRecord(m->ev_free[b], st));
   m->ev_free_valid[b] = true;
@@ -959,23 +1100,36 @@ extern "C" int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream) {
 
 extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
                                       const float* T3, int32_t submap, void* stream) {
+  return tslam_tsdf_queue_depth_tex(m, depth_host, nullptr, h, w, 0, 0, R9, T3, submap, stream);
+}
+extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth_host, const uint8_t* tex_host, int32_t h, int32_t w,
+                                          int32_t th, int32_t tw, const float* R9, const float* T3, int32_t submap, void* stream) {
+  if (m) { int rc0 = ts_check_tex(m, tex_host, th, tw); if (rc0) return rc0; }
   if (!m || !depth_host || !R9 || !T3 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
   if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
   if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (m->q_n > 0 && (m->q_h != h || m->q_w != w)) {
+  const int has_tex = tex_host != nullptr;
+  if (!has_tex) { th = 0; tw = 0; }
+  // one batch = one frame geometry and either all or no frames textured
+  if (m->q_n > 0 && (m->q_h != h || m->q_w != w || m->q_has_tex != has_tex || m->q_th != th || m->q_tw != tw)) {
     int rc = ts_launch_queue(m, st);
     if (rc) return rc;
   }
   const int b = m->q_buf, q = m->q_n;
   if (q == 0) {
     m->q_h = h; m->q_w = w;
+    m->q_has_tex = has_tex; m->q_th = th; m->q_tw = tw;
     if (m->ev_free_valid[b]) TS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_free[b], 0));  // kernels that read this buffer are done
   }
   // One linear copy of the whole frame.  (A strided 2-D copy of only the sampled rows halves the bytes but was
   // measured SLOWER from pinned memory: 30.2 k vs 36.5 k frames/s end to end - 240 row descriptors of 1280 B.)
   uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
   TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  if (has_tex) {
+    uint8_t* tdst = m->tex_stage + ((size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * th * tw) * 3;
+    TS_CUDA(cudaMemcpyAsync(tdst, tex_host, (size_t)th * tw * 3, cudaMemcpyHostToDevice, m->copy_stream));
+  }
   memcpy(m->q_R + 9 * q, R9, 36);
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;
@@ -1024,7 +1178,7 @@ __device__ __forceinline__ int warp_append_i32(bool want, int* counter) {
 }
 
 __global__ void __launch_bounds__(256) k_gather(TsGrid g, int submap, long long cap, int32_t* idx, float* tsdf, float* wts,
-                                                 int8_t* occ, unsigned long long* counter) {
+                                                 int8_t* occ, float* color, unsigned long long* counter) {
   const int nb = min(*g.n_blocks, g.max_blocks);
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
     int s, bx, by, bz;
@@ -1042,13 +1196,17 @@ __global__ void __launch_bounds__(256) k_gather(TsGrid g, int submap, long long 
         tsdf[row] = t.x;
         wts[row] = t.y;
         occ[row] = g.occ[base + v];
+        if (color) {  // :437-440
+          const float4 c = g.col ? g.col[base + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+          color[3 * row] = c.x; color[3 * row + 1] = c.y; color[3 * row + 2] = c.z;
+        }
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) k_scatter(TsGrid g, int submap, long long n, const int32_t* idx, const float* tsdf,
-                                                  const float* wts, const int8_t* occ) {
+                                                  const float* wts, const int8_t* occ, const float* color) {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
     const int i = idx[3 * r], j = idx[3 * r + 1], k = idx[3 * r + 2];
     if (!ts_in_bounds(g, i, j, k)) continue;
@@ -1058,6 +1216,7 @@ __global__ void __launch_bounds__(256) k_scatter(TsGrid g, int submap, long long
     g.tw[o] = make_float2(tsdf[r], wts[r]);  // :447-448
     g.occ[o] = occ[r];                        // :449
     g.obs[o] = 1;                             // :454
+    if (color && g.col) g.col[o] = make_float4(color[3 * r], color[3 * r + 1], color[3 * r + 2], 0.0f);  // :450-453
   }
 }
 
@@ -1078,13 +1237,17 @@ extern "C" int tslam_tsdf_count_active(tslam_tsdf_t* m, int32_t submap, int64_t*
 
 extern "C" int tslam_tsdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* tsdf, float* w, int8_t* occ,
                                  int64_t* n_out, void* stream) {
+  return tslam_tsdf_gather2(m, submap, cap, idx, tsdf, w, occ, nullptr, n_out, stream);
+}
+extern "C" int tslam_tsdf_gather2(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* tsdf, float* w, int8_t* occ,
+                                  float* color, int64_t* n_out, void* stream) {
   if (!m || !n_out) return TSLAM_E_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = ts_flush_pending(m, st);
   if (rc) return rc;
   unsigned long long* ctr = (unsigned long long*)(m->scratch_i + 8);
   TS_CUDA(cudaMemsetAsync(ctr, 0, 8, st));
-  k_gather<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, cap, idx, tsdf, w, occ, ctr);
+  k_gather<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, cap, idx, tsdf, w, occ, color, ctr);
   TS_LAUNCH_CHECK(m);
   unsigned long long v = 0;
   TS_CUDA(cudaMemcpyAsync(&v, ctr, 8, cudaMemcpyDeviceToHost, st));
@@ -1098,6 +1261,10 @@ extern "C" int tslam_tsdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, i
 
 extern "C" int tslam_tsdf_scatter(tslam_tsdf_t* m, int32_t submap, int64_t n, const int32_t* idx, const float* tsdf, const float* w,
                                   const int8_t* occ, void* stream) {
+  return tslam_tsdf_scatter2(m, submap, n, idx, tsdf, w, occ, nullptr, stream);
+}
+extern "C" int tslam_tsdf_scatter2(tslam_tsdf_t* m, int32_t submap, int64_t n, const int32_t* idx, const float* tsdf, const float* w,
+                                   const int8_t* occ, const float* color, void* stream) {
   if (!m || n < 0 || submap < 0 || submap >= m->cfg.max_submaps) return TSLAM_E_INVALID;
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1105,7 +1272,7 @@ extern "C" int tslam_tsdf_scatter(tslam_tsdf_t* m, int32_t submap, int64_t n, co
   if (rc) return rc;
   int grid = (int)((n + 255) / 256);
   if (grid > m->sm_count * 32) grid = m->sm_count * 32;
-  k_scatter<<<grid, 256, 0, st>>>(m->g, submap, n, idx, tsdf, w, occ);
+  k_scatter<<<grid, 256, 0, st>>>(m->g, submap, n, idx, tsdf, w, occ, color);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }
@@ -1146,7 +1313,10 @@ __global__ void __launch_bounds__(256) k_extract_surface(TsGrid g, int submap, i
       const int row = warp_append_i32(want, counter);  // :358
       if (want && row < cap) {                         // :359 (saturating)
         xyz[3 * (size_t)row] = x; xyz[3 * (size_t)row + 1] = y; xyz[3 * (size_t)row + 2] = z;
-        if (rgb) {
+        if (rgb && g.col) {  // enable_texture: the voxel's own colour (:360-362)
+          const float4 c = g.col[base + v];
+          rgb[3 * (size_t)row] = c.x; rgb[3 * (size_t)row + 1] = c.y; rgb[3 * (size_t)row + 2] = c.z;
+        } else if (rgb) {
           const int ci = (int)fmaxf(fminf(((z - fl) / (ce - fl)) * 1023.0f, 1023.0f), 0.0f);  // mapping_common.py:216-219
           rgb[3 * (size_t)row] = cmap[3 * ci]; rgb[3 * (size_t)row + 1] = cmap[3 * ci + 1]; rgb[3 * (size_t)row + 2] = cmap[3 * ci + 2];
         }
@@ -1251,6 +1421,9 @@ __global__ void __launch_bounds__(256) k_fuse(TsGrid dst, TsGrid src, const floa
       if (!(src.obs[base + v] > 0)) continue;  // :292
       const float2 t = src.tw[base + v];
       const int occ = src.occ[base + v];
+      const bool tex = dst.col != nullptr && src.col != nullptr;
+      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tex) sc = src.col[base + v];
       const float lx = (float)(bx * TS_B + (v >> 8)) * vs, ly = (float)(by * TS_B + ((v >> 4) & 15)) * vs,
                   lz = (float)(bz * TS_B + (v & 15)) * vs;
       const float gx = (((R[0] * lx + R[1] * ly) + R[2] * lz) + T[0]) / vs;  // :293-294
@@ -1272,6 +1445,10 @@ __global__ void __launch_bounds__(256) k_fuse(TsGrid dst, TsGrid src, const floa
         const size_t o = (size_t)cur_blk * TS_B3 + ts_voxel_off(ci, cj, ck);
         const float w = t.y * wt;                    // :307
         red_add_f32x2(&dst.acc[o], w * t.x, w);      // :274-275
+        if (tex) {                                   // :276-277: sum w*c here, / sum w at commit
+          float* dc = (float*)&dst.col[o];
+          atomicAdd(dc, w * sc.x); atomicAdd(dc + 1, w * sc.y); atomicAdd(dc + 2, w * sc.z);
+        }
         if (dst.obs[o] == 0) dst.obs[o] = 2;         // :279 observed, value pending (2 -> 1 at commit)
         sat_add_i8(&dst.occ[o], occ);                // :280
       }

@@ -89,6 +89,8 @@ class TiledGlobalMap:
     """A DenseTSDF global map whose volume is tiled over the ranks of a torch.distributed group."""
 
     def __init__(self, global_map, dist, rank, world, tiles=None):
+        if getattr(global_map, "enable_texture", False):
+            raise NotImplementedError("TiledGlobalMap exchanges geometry planes only; textured global maps are single-GPU")
         self.m = global_map
         self.dist = dist
         self.rank, self.world = int(rank), int(world)

@@ -51,18 +51,19 @@ class DenseTSDF(BaseMap):
         self.recast_step = recast_step
         self.color_same_proj = color_same_proj
         self.clear_last_TSDF_exporting = False  # assigned by SubmapMapping (submap_mapping.py:134)
-        self.color = None  # texture path not built yet (second priority); geometry only
-        if texture_enabled:
-            print("[DenseTSDF/b200] texture_enabled=True: colour fusion is not implemented yet, geometry only")
+        self.color = None  # the colour plane lives inside the library handle (dense_tsdf.py:48-50); read it with to_numpy
 
         self._h = TsdfHandle(self.N, self.Nz, voxel_scale=voxel_scale, max_ray_length=max_ray_length,
                              min_ray_length=min_ray_length, internal_voxels=internal_voxels, recast_step=recast_step,
                              K=None, is_global_map=is_global_map, disp_floor=disp_floor, disp_ceiling=disp_ceiling,
                              max_submaps=min(max_submap_num, 1024), max_blocks=max_blocks,
-                             max_image_pixels=max_image_pixels)
+                             max_image_pixels=max_image_pixels, texture_enabled=texture_enabled)
         self.initialize_submap_fields(self.max_submap_num)
         self._init_export_fields()
         self._queue = self._h.L.tslam_tsdf_queue_depth
+        self._queue_tex = self._h.L.tslam_tsdf_queue_depth_tex
+        if texture_enabled:
+            self._h.set_color_intrinsics([1, 0, 0, 0, 1, 0, 0, 0, 1], color_same_proj)
         self._pR, self._pT = self.input_R_np.ctypes.data, self.input_T_np.ctypes.data  # persistent pose buffers (BaseMap.set_pose)
         print(f"TSDF map initialized blocks {self.block_num_xy}x{self.block_num_xy}x{self.block_num_z}")
 
@@ -84,6 +85,11 @@ class DenseTSDF(BaseMap):
         self._flush()
         self._h.set_intrinsics(self.K_cam_dep)
 
+    def set_color_camera_intrinsic(self, K):
+        super(DenseTSDF, self).set_color_camera_intrinsic(K)
+        self._flush()
+        self._h.set_color_intrinsics(self.K_cam_color, self.color_same_proj)
+
     def _upload_submap_pose(self, submap_id, R, T):
         self._h.set_submap_pose(submap_id, R, T)
 
@@ -98,7 +104,18 @@ class DenseTSDF(BaseMap):
             depthmap = np.ascontiguousarray(depthmap, dtype=np.uint16)
         h, w = depthmap.shape
         sid = 0 if self.is_global_map else self.active_submap_id.v
-        rc = self._queue(self._h.h, depthmap.__array_interface__["data"][0], h, w, self._pR, self._pT, sid, self._stream_ptr())
+        if self.enable_texture:  # ti.static(self.enable_texture) (:205): the colour image rides along (uint8 [th,tw,3])
+            if not self.color_same_proj and self.K_cam_color is None:
+                raise RuntimeError("set_color_camera_intrinsic() must be called before recast_depth_to_map (color_same_proj=False)")
+            if texture.dtype != np.uint8 or not texture.flags.c_contiguous:
+                texture = np.ascontiguousarray(texture, dtype=np.uint8)
+            th, tw = texture.shape[0], texture.shape[1]
+            if self.color_same_proj and (th < h or tw < w):
+                raise ValueError("color_same_proj=True needs a colour image at least as large as the depth image")
+            rc = self._queue_tex(self._h.h, depthmap.__array_interface__["data"][0], texture.__array_interface__["data"][0], h, w,
+                                 th, tw, self._pR, self._pT, sid, self._stream_ptr())
+        else:
+            rc = self._queue(self._h.h, depthmap.__array_interface__["data"][0], h, w, self._pR, self._pT, sid, self._stream_ptr())
         if rc:
             capi.check(rc)
 
@@ -114,7 +131,10 @@ class DenseTSDF(BaseMap):
         self.set_pose(R, T)
         xyz = np.ascontiguousarray(np.asarray(xyz_array, dtype=np.float32).reshape(-1, 3))
         s = 0 if self.is_global_map else self.active_submap_id[None]
-        self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=s, commit=True)
+        rgb = None
+        if self.enable_texture:  # :179-183
+            rgb = np.ascontiguousarray(np.asarray(rgb_array, dtype=np.uint8).reshape(-1, 3))
+        self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=s, commit=True, rgb=rgb)
         self._torch.cuda.current_stream().synchronize()  # pageable source
 
     # ------------------------------------------------------------------ submaps / fusion (:272-318)
@@ -176,18 +196,26 @@ class DenseTSDF(BaseMap):
     def to_numpy(self, data_indices, data_tsdf, data_wtsdf, data_occ, data_color):
         """Fill caller arrays (dtypes of export_submap, :459-462) with the observed voxels of the active submap."""
         self._flush()
-        idx, t, w, occ = self._h.gather(self._active())
+        if self.enable_texture:
+            idx, t, w, occ, col = self._h.gather(self._active(), color=True)
+        else:
+            idx, t, w, occ = self._h.gather(self._active())
         n = idx.shape[0]
         data_indices[:n] = idx
         data_tsdf[:n] = t
         data_wtsdf[:n] = w
         data_occ[:n] = occ
+        if self.enable_texture:  # :437-440
+            data_color[:n] = col
 
     def load_numpy(self, submap_id, data_indices, data_tsdf, data_wtsdf, data_occ, data_color):
         self._flush()
         occ = np.clip(np.asarray(data_occ).astype(np.int64), -128, 127).astype(np.int8)
+        col = None
+        if self.enable_texture:  # :450-453
+            col = np.asarray(data_color, dtype=np.float32).reshape(-1, 3)
         self._h.scatter(submap_id, np.asarray(data_indices).astype(np.int32), np.asarray(data_tsdf, dtype=np.float32),
-                        np.asarray(data_wtsdf, dtype=np.float32), occ)
+                        np.asarray(data_wtsdf, dtype=np.float32), occ, color=col)
 
     def export_submap(self):
         s = time.time()
@@ -196,7 +224,7 @@ class DenseTSDF(BaseMap):
         tsdf = np.zeros((num), np.float16)
         w_tsdf = np.zeros((num), np.float16)
         occupy = np.zeros((num), np.int8)
-        color = np.array([])
+        color = np.zeros((num, 3), np.float16) if self.enable_texture else np.array([])  # :463-466
         self.to_numpy(indices, tsdf, w_tsdf, occupy, color)
         obj = {
             'indices': indices,
@@ -230,7 +258,8 @@ class DenseTSDF(BaseMap):
         self.remote_submap_num[None] = self.remote_submap_num[None] + 1
         idx = self.max_submap_num - self.remote_submap_num[None]
         R, T = submap['pose']
-        self.load_numpy(idx, submap['indices'], submap['TSDF'], submap['W_TSDF'], submap['occupy'], np.array([]))
+        color = submap['color'] if self.enable_texture else np.array([])  # :509-512
+        self.load_numpy(idx, submap['indices'], submap['TSDF'], submap['W_TSDF'], submap['occupy'], color)
         self.set_base_pose_submap(idx, R, T)
         return idx
 

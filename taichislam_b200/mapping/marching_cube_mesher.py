@@ -1,5 +1,5 @@
 """MarchingCubeMesher - the reference's class surface (marching_cube_mesher.py:12-193) on the
-two-pass CUDA marching cubes of libtslam.so (tslam_mc_generate)."""
+two-pass CUDA marching cubes of libtslam.so (tslam_mc_generate2)."""
 import ctypes as C
 
 from .. import _capi as capi
@@ -29,9 +29,10 @@ class MarchingCubeMesher:
         m = self.mapping
         m._flush()
         n = C.c_int64(0)
-        rc = m._h.L.tslam_mc_generate(m._h.h, int(step), float(self.tsdf_surface_thres), self.max_triangles,
-                                      capi.tptr(self.mesh_vertices.t), capi.tptr(self.mesh_normals.t), C.byref(n),
-                                      capi.stream_ptr())
+        colors = capi.tptr(self.mesh_colors.t) if self.enable_texture else None  # add_triangle_color (:104-108, :120-125)
+        rc = m._h.L.tslam_mc_generate2(m._h.h, int(step), float(self.tsdf_surface_thres), self.max_triangles,
+                                       capi.tptr(self.mesh_vertices.t), capi.tptr(self.mesh_normals.t), colors, C.byref(n),
+                                       capi.stream_ptr())
         if rc != capi.E_CAPACITY:
             capi.check(rc)
         self.num_facelets[None] = int(n.value)

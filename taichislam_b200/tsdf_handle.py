@@ -13,7 +13,7 @@ from . import _capi as capi
 class TsdfHandle:
     def __init__(self, N, Nz, voxel_scale=0.05, max_ray_length=10.0, min_ray_length=0.3, internal_voxels=10,
                  recast_step=2, K=None, is_global_map=False, disp_floor=-0.3, disp_ceiling=1.8, max_submaps=1024,
-                 max_blocks=0, max_image_pixels=0, max_points=0):
+                 max_blocks=0, max_image_pixels=0, max_points=0, texture_enabled=False):
         capi.require_gpu()
         import torch  # device buffers / streams only
         self.torch = torch
@@ -21,7 +21,8 @@ class TsdfHandle:
         K = K if K is not None else [1, 0, 0, 0, 1, 0, 0, 0, 1]
         self.cfg = capi.TsdfConfig(voxel_scale, N, Nz, max_ray_length, min_ray_length, internal_voxels, recast_step,
                                    K[0], K[4], K[2], K[5], int(is_global_map), disp_floor, disp_ceiling,
-                                   max_submaps, max_blocks, max_image_pixels, max_points)
+                                   max_submaps, max_blocks, max_image_pixels, max_points, int(bool(texture_enabled)))
+        self.texture_enabled = bool(texture_enabled)
         h = C.c_void_p()
         torch.cuda.init()
         torch.cuda.current_stream()  # make sure the primary context exists and is current
@@ -48,13 +49,18 @@ class TsdfHandle:
     def set_intrinsics(self, K9):
         capi.check(self.L.tslam_tsdf_set_intrinsics(self.h, K9[0], K9[4], K9[2], K9[5]))
 
+    def set_color_intrinsics(self, K9, color_same_proj=False):
+        """set_color_camera_intrinsic (mapping_common.py:28-29) + color_same_proj (dense_tsdf.py:16)."""
+        capi.check(self.L.tslam_tsdf_set_color_intrinsics(self.h, K9[0], K9[4], K9[2], K9[5], int(bool(color_same_proj))))
+
     def set_submap_pose(self, s, R, T):
         R, T = capi.f32c(R).reshape(9), capi.f32c(T).reshape(3)
         capi.check(self.L.tslam_tsdf_set_submap_pose(self.h, int(s), capi.np_ptr(R), capi.np_ptr(T)))
 
     # -- integrate ------------------------------------------------------------------------
-    def integrate_depth(self, depth, Rs, Ts, submaps=None, commit=True):
-        """depth: uint16 [n,h,w] (or [h,w]) numpy (host) or torch CUDA tensor; Rs [n,3,3]; Ts [n,3]."""
+    def integrate_depth(self, depth, Rs, Ts, submaps=None, commit=True, texture=None):
+        """depth: uint16 [n,h,w] (or [h,w]) numpy (host) or torch CUDA tensor; Rs [n,3,3]; Ts [n,3];
+        texture: uint8 [n,th,tw,3] in the same memory space as depth (textured maps)."""
         torch = self.torch
         if isinstance(depth, torch.Tensor):
             assert depth.is_cuda and depth.dtype in (torch.uint16, torch.int16) and depth.is_contiguous()
@@ -70,11 +76,26 @@ class TsdfHandle:
         sm = None
         if submaps is not None:
             sm = np.ascontiguousarray(np.broadcast_to(np.asarray(submaps, dtype=np.int32), (n,)))
+        if texture is not None:
+            if isinstance(texture, torch.Tensor):
+                assert mem == capi.MEM_DEVICE and texture.is_cuda and texture.dtype == torch.uint8 and texture.is_contiguous()
+                tptr, tshape = capi.tptr(texture), tuple(texture.shape)
+            else:
+                assert mem == capi.MEM_HOST
+                texture = np.ascontiguousarray(texture, dtype=np.uint8)
+                tptr, tshape = capi.np_ptr(texture), texture.shape
+            if len(tshape) == 3:
+                tshape = (1,) + tuple(tshape)
+            assert tshape[0] == n and tshape[3] == 3
+            capi.check(self.L.tslam_tsdf_integrate_depth_tex(self.h, ptr, tptr, mem, n, h, w, tshape[1], tshape[2], capi.np_ptr(Rs),
+                                                             capi.np_ptr(Ts), capi.np_ptr(sm) if sm is not None else None,
+                                                             capi.F_COMMIT if commit else 0, capi.stream_ptr()))
+            return
         capi.check(self.L.tslam_tsdf_integrate_depth(self.h, ptr, mem, n, h, w, capi.np_ptr(Rs), capi.np_ptr(Ts),
                                                      capi.np_ptr(sm) if sm is not None else None,
                                                      capi.F_COMMIT if commit else 0, capi.stream_ptr()))
 
-    def integrate_points(self, xyz, R, T, submap=0, commit=True):
+    def integrate_points(self, xyz, R, T, submap=0, commit=True, rgb=None):
         torch = self.torch
         if isinstance(xyz, torch.Tensor):
             assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
@@ -83,6 +104,18 @@ class TsdfHandle:
             xyz = np.ascontiguousarray(xyz, dtype=np.float32)
             mem, ptr, n = capi.MEM_HOST, capi.np_ptr(xyz), xyz.shape[0]
         R, T = capi.f32c(R).reshape(9), capi.f32c(T).reshape(3)
+        if rgb is not None:
+            if isinstance(rgb, torch.Tensor):
+                assert mem == capi.MEM_DEVICE and rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+                cptr = capi.tptr(rgb)
+            else:
+                assert mem == capi.MEM_HOST
+                rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+                cptr = capi.np_ptr(rgb)
+            assert tuple(rgb.shape) == (n, 3)
+            capi.check(self.L.tslam_tsdf_integrate_points_rgb(self.h, ptr, cptr, mem, n, capi.np_ptr(R), capi.np_ptr(T), int(submap),
+                                                              capi.F_COMMIT if commit else 0, capi.stream_ptr()))
+            return
         capi.check(self.L.tslam_tsdf_integrate_points(self.h, ptr, mem, n, capi.np_ptr(R), capi.np_ptr(T), int(submap),
                                                       capi.F_COMMIT if commit else 0, capi.stream_ptr()))
 
@@ -99,8 +132,9 @@ class TsdfHandle:
         capi.check(self.L.tslam_tsdf_count_active(self.h, int(submap), C.byref(n)))
         return int(n.value)
 
-    def gather_device(self, submap=0, cap=None):
-        """Observed voxels of `submap` as torch CUDA tensors (idx int32[n,3], tsdf, w f32[n], occ int8[n])."""
+    def gather_device(self, submap=0, cap=None, color=False):
+        """Observed voxels of `submap` as torch CUDA tensors (idx int32[n,3], tsdf, w f32[n], occ int8[n]
+        [, color f32[n,3]])."""
         torch = self.torch
         if cap is None:
             cap = self.count_active(submap)
@@ -110,16 +144,21 @@ class TsdfHandle:
         w = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
         occ = torch.empty(max(cap, 1), dtype=torch.int8, device=dev)
         n = C.c_int64(0)
+        if color:
+            col = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=dev)
+            capi.check(self.L.tslam_tsdf_gather2(self.h, int(submap), cap, capi.tptr(idx), capi.tptr(t), capi.tptr(w),
+                                                 capi.tptr(occ), capi.tptr(col), C.byref(n), capi.stream_ptr()))
+            k = int(n.value)
+            return idx[:k], t[:k], w[:k], occ[:k], col[:k]
         capi.check(self.L.tslam_tsdf_gather(self.h, int(submap), cap, capi.tptr(idx), capi.tptr(t), capi.tptr(w),
                                             capi.tptr(occ), C.byref(n), capi.stream_ptr()))
         k = int(n.value)
         return idx[:k], t[:k], w[:k], occ[:k]
 
-    def gather(self, submap=0):
-        idx, t, w, occ = self.gather_device(submap)
-        return idx.cpu().numpy(), t.cpu().numpy(), w.cpu().numpy(), occ.cpu().numpy()
+    def gather(self, submap=0, color=False):
+        return tuple(a.cpu().numpy() for a in self.gather_device(submap, color=color))
 
-    def scatter(self, submap, idx, tsdf, w, occ):
+    def scatter(self, submap, idx, tsdf, w, occ, color=None):
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
 
@@ -132,8 +171,13 @@ class TsdfHandle:
         tsdf, w = dv(tsdf, torch.float32), dv(w, torch.float32)
         occ = dv(occ, torch.int8)
         n = idx.shape[0]
-        capi.check(self.L.tslam_tsdf_scatter(self.h, int(submap), n, capi.tptr(idx), capi.tptr(tsdf), capi.tptr(w),
-                                             capi.tptr(occ), capi.stream_ptr()))
+        if color is not None:
+            color = dv(color, torch.float32).reshape(n, 3)
+            capi.check(self.L.tslam_tsdf_scatter2(self.h, int(submap), n, capi.tptr(idx), capi.tptr(tsdf), capi.tptr(w),
+                                                  capi.tptr(occ), capi.tptr(color), capi.stream_ptr()))
+        else:
+            capi.check(self.L.tslam_tsdf_scatter(self.h, int(submap), n, capi.tptr(idx), capi.tptr(tsdf), capi.tptr(w),
+                                                 capi.tptr(occ), capi.stream_ptr()))
         torch.cuda.current_stream().synchronize()  # the temporaries above must outlive the kernel
 
     def fuse_from(self, src):
@@ -170,17 +214,24 @@ class TsdfHandle:
         k = min(n, cap)
         return n, xyz[:k].cpu().numpy(), val[:k].cpu().numpy()
 
-    def marching_cubes(self, step=1, thres=0.1, cap_tri=1 << 21):
+    def marching_cubes(self, step=1, thres=0.1, cap_tri=1 << 21, color=False):
         torch = self.torch
         dev = torch.device("cuda", torch.cuda.current_device())
         v = torch.empty((3 * cap_tri, 3), dtype=torch.float32, device=dev)
         nrm = torch.empty((3 * cap_tri, 3), dtype=torch.float32, device=dev)
         n = C.c_int64(0)
-        rc = self.L.tslam_mc_generate(self.h, int(step), float(thres), cap_tri, capi.tptr(v), capi.tptr(nrm), C.byref(n),
-                                      capi.stream_ptr())
+        if color:
+            col = torch.empty((3 * cap_tri, 3), dtype=torch.float32, device=dev)
+            rc = self.L.tslam_mc_generate2(self.h, int(step), float(thres), cap_tri, capi.tptr(v), capi.tptr(nrm), capi.tptr(col),
+                                           C.byref(n), capi.stream_ptr())
+        else:
+            rc = self.L.tslam_mc_generate(self.h, int(step), float(thres), cap_tri, capi.tptr(v), capi.tptr(nrm), C.byref(n),
+                                          capi.stream_ptr())
         if rc != capi.E_CAPACITY:
             capi.check(rc)
         k = min(int(n.value), cap_tri)
+        if color:
+            return int(n.value), v[:3 * k].cpu().numpy(), nrm[:3 * k].cpu().numpy(), col[:3 * k].cpu().numpy()
         return int(n.value), v[:3 * k].cpu().numpy(), nrm[:3 * k].cpu().numpy()
 
     # -- planner queries (batched @ti.func helpers of BaseMap, mapping_common.py:165-204) ------------------

@@ -217,3 +217,53 @@ def test_reference_fixtures_full_counts():
         m = OracleTSDF(map_scale=list(obj["map_scale"]), voxel_scale=float(obj["voxel_size"]), is_global_map=True)
         m.scatter(0, obj["indices"], obj["TSDF"].astype(np.float32), obj["W_TSDF"].astype(np.float32), obj["occupy"])
         assert m.count_active() == obj["TSDF"].shape[0]
+
+
+def test_texture_known_answers():
+    """Texture rule of the oracle (dense_tsdf.py:205-213, :233-234, :268-269) on cases with a closed-form answer:
+    a uniformly coloured image colours every touched voxel with the 10-bit quantised mean; a second frame overwrites
+    the voxels it touches (later frame wins) and only those; color_ind_from_depth_pt's out-of-range pixels read
+    texture[0,0] (mapping_common.py:56-57)."""
+    def q10(v):
+        return np.float32(int(np.float32(v) / np.float32(255.0) * np.float32(1023.0) + np.float32(0.5))) / np.float32(1023.0)
+
+    d = syn.scene_plane(3.0)
+    m = OracleTSDF(map_scale=[12.8, 12.8], K=syn.K_DEPTH, is_global_map=True, disp_ceiling=5.0)
+    m.set_color(True, True)
+    tex = np.zeros((480, 640, 3), np.uint8)
+    tex[:] = (200, 40, 90)
+    m.integrate_depth_tex(np.eye(3), np.zeros(3), d, tex)
+    idx, t, w, occ = m.gather(0)
+    col = m.gather_color(0)
+    assert len(col) == GOLD["integrate_256"]["S1_plane3m"]["active"]
+    assert np.all(col == np.array([q10(200), q10(40), q10(90)], np.float32))
+    # second frame: a narrower depth image region (left half valid) in another colour
+    d2 = d.copy()
+    d2[:, 320:] = 0
+    tex2 = np.zeros_like(tex)
+    tex2[:] = (10, 250, 30)
+    m.integrate_depth_tex(np.eye(3), np.zeros(3), d2, tex2)
+    idx2, _, w2, _ = m.gather(0)
+    col2 = m.gather_color(0)
+    # the half image cuts some buckets at column 320 -> a few rays (and voxels) of its own; compare on the first set
+    pos = {tuple(r): q for q, r in enumerate(idx2)}
+    sel = np.array([pos[tuple(r)] for r in idx])
+    assert len(idx2) - len(idx) < 50
+    w2, col2 = w2[sel], col2[sel]
+    grew = w2 > w  # voxels the second frame touched (W below the clamp everywhere but next to the sensor)
+    new = np.all(col2 == np.array([q10(10), q10(250), q10(30)], np.float32), axis=1)
+    old = np.all(col2 == col, axis=1)
+    assert np.all(new | old) and new.sum() > 1000 and old.sum() > 1000
+    assert np.all(new[grew]) and not np.any(new & ~grew & (w < 999))
+    # colour camera with a tiny image: every projected pixel falls outside -> texture[0,0]
+    m3 = OracleTSDF(map_scale=[12.8, 12.8], K=syn.K_DEPTH, is_global_map=True)
+    m3.set_color(True, False, [syn.FX, 0, 5000.0, 0, syn.FY, 5000.0, 0, 0, 1])
+    tex3 = np.full((8, 8, 3), 77, np.uint8)
+    tex3[0, 0] = (255, 1, 128)
+    m3.integrate_depth_tex(np.eye(3), np.zeros(3), d, tex3)
+    assert np.all(m3.gather_color(0) == np.array([q10(255), q10(1), q10(128)], np.float32))
+    # coloured surface export + mesh colours stay inside the colour gamut of the map
+    n, xyz, rgb = m.surface(0)
+    assert n > 0 and set(map(tuple, np.unique(rgb, axis=0))) <= set(map(tuple, np.unique(col2, axis=0)))
+    nt, v, nrm, c = m.marching_cubes_color(1, 0.1)
+    assert nt > 1000 and c.min() >= 0.0 and c.max() <= 1.0 and (c[:, 1] > 0).all()

@@ -244,6 +244,7 @@ typedef struct tslam_octo_config {
   int32_t max_blocks;       /* capacity of the 8^3 counter-block pool (0 = derive)     */
   int32_t max_image_pixels;
   int32_t max_points;
+  int32_t texture_enabled;  /* taichi_octomap.py:34,77-79: per-voxel colour                */
 } tslam_octo_config_t;
 
 int tslam_octo_create(const tslam_octo_config_t* cfg, tslam_octo_t** out);
@@ -258,6 +259,20 @@ int tslam_octo_integrate_points(tslam_octo_t* m, const float* xyz, int mem, int3
 /* recast_depth_to_map_kernel (taichi_octomap.py:147-169). */
 int tslam_octo_integrate_depth(tslam_octo_t* m, const uint16_t* depth, int mem, int32_t h, int32_t w, const float* R9,
                                const float* T3, int32_t submap, void* stream);
+/* Textured octomaps (texture_enabled): process_point overwrites color[ijk] with the point's colour, channels swapped
+ * BGR -> RGB, /255 (taichi_octomap.py:120-124); racing points, last writer wins.  Deterministic here: the latest
+ * integrate call wins, inside a call the largest packed RGB.  rgb uint8 [n,3] / tex uint8 [th,tw,3] in `mem` space;
+ * NULL colours integrate hits only.  Fusion copies the colour of the most recently integrated source voxel (:189). */
+int tslam_octo_set_color_intrinsics(tslam_octo_t* m, double fx, double fy, double cx, double cy, int color_same_proj);
+int tslam_octo_integrate_points_rgb(tslam_octo_t* m, const float* xyz, const uint8_t* rgb, int mem, int32_t n, const float* R9,
+                                    const float* T3, int32_t submap, void* stream);
+int tslam_octo_integrate_depth_tex(tslam_octo_t* m, const uint16_t* depth, const uint8_t* tex, int mem, int32_t h, int32_t w,
+                                   int32_t th, int32_t tw, const float* R9, const float* T3, int32_t submap, void* stream);
+/* gather / LoD export with the colour column: color f32[cap,3] / rgb f32[cap,3] DEVICE or NULL (:101-102, :113-114). */
+int tslam_octo_gather2(tslam_octo_t* m, int32_t submap, int64_t cap, int32_t* idx, uint32_t* count, float* color, int64_t* n_out,
+                       void* stream);
+int tslam_octo_extract2(tslam_octo_t* m, int32_t submap, int32_t level, int64_t cap, float* xyz, float* rgb, int32_t* count_dev,
+                        void* stream);
 /* every (i,j,k,count>0) of `submap`: idx int32[cap,3], count uint32[cap] (DEVICE). Synchronises. */
 int tslam_octo_gather(tslam_octo_t* m, int32_t submap, int64_t cap, int32_t* idx, uint32_t* count, int64_t* n_out,
                       void* stream);

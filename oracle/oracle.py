@@ -84,6 +84,12 @@ def lib():
         L.orc_octo_export.argtypes = [vp, i32, i32, i64, vp]
         L.orc_octo_export.restype = i64
         L.orc_octo_fuse.argtypes = [vp, vp]
+        L.orc_octo_set_color.argtypes = [vp, i32, i32, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_octo_integrate_points_rgb.argtypes = [vp, vp, vp, i32, vp, vp, i32]
+        L.orc_octo_integrate_depth_tex.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32]
+        L.orc_octo_gather_color.argtypes = [vp, i32, i64, vp]
+        L.orc_octo_export2.argtypes = [vp, i32, i32, i64, vp, vp]
+        L.orc_octo_export2.restype = i64
         L.orc_tsdf_set_color.argtypes = [vp, i32, i32, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_tsdf_integrate_depth_tex.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]
         L.orc_tsdf_integrate_points_rgb.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32]
@@ -317,6 +323,36 @@ class OracleOctomap:
         xyz = np.zeros((cap, 3), np.float32)
         n = int(lib().orc_octo_export(self.h, submap, level, cap, _p(xyz)))
         return n, xyz[:min(n, cap)]
+
+    # -- texture (taichi_octomap.py:77-79, :120-124, :160-167, :189) --
+    def set_color(self, enabled=True, same_proj=True, Kcolor=None):
+        K = Kcolor if Kcolor is not None else [1, 0, 0, 0, 1, 0, 0, 0, 1]
+        lib().orc_octo_set_color(self.h, int(enabled), int(same_proj), K[0], K[4], K[2], K[5])
+
+    def integrate_points_rgb(self, R, T, xyz, rgb, submap=0):
+        xyz = _f32(xyz)
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        R, T = _f32(R), _f32(T)
+        lib().orc_octo_integrate_points_rgb(self.h, _p(xyz), _p(rgb), xyz.shape[0], _p(R), _p(T), submap)
+
+    def integrate_depth_tex(self, R, T, depth, texture, submap=0):
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        texture = np.ascontiguousarray(texture, dtype=np.uint8)
+        R, T = _f32(R), _f32(T)
+        lib().orc_octo_integrate_depth_tex(self.h, _p(depth), _p(texture), texture.shape[0], texture.shape[1], depth.shape[0],
+                                           depth.shape[1], _p(R), _p(T), submap)
+
+    def gather_color(self, submap=0):
+        n = int(lib().orc_octo_gather(self.h, submap, 0, None, None))
+        c = np.zeros((n, 3), np.float32)
+        lib().orc_octo_gather_color(self.h, submap, n, _p(c))
+        return c
+
+    def export_color(self, level=1, submap=0, cap=1 << 22):
+        xyz = np.zeros((cap, 3), np.float32)
+        rgb = np.zeros((cap, 3), np.float32)
+        n = int(lib().orc_octo_export2(self.h, submap, level, cap, _p(xyz), _p(rgb)))
+        return n, xyz[:min(n, cap)], rgb[:min(n, cap)]
 
     def fuse_from(self, src):
         lib().orc_octo_fuse(self.h, src.h)

@@ -435,6 +435,17 @@ struct Octo {
   double fx, fy, cx, cy;
   int min_occupy_thres;
   std::map<Key, uint32_t> cnt;  // (s,i,j,k) -> hits; std::map => sorted export
+  // texture (taichi_octomap.py:77-79, :120-124): the reference overwrites color[ijk] per point, racing, last writer
+  // wins.  Canonical: per voxel the largest word [integrate-call sequence number : 22 | r:8 | g:8 | b:8] (colour
+  // after the BGR->RGB swap of :121-124) - the latest call wins, inside a call the largest packed colour.
+  bool tex_enabled = false, color_same_proj = true;
+  float fxc = 1, fyc = 1, cxc = 0, cyc = 0;
+  uint32_t frame_seq = 0;
+  std::map<Key, uint64_t> cw;
+  void hit(const Key& k, uint32_t add, uint64_t word) {
+    cnt[k] += add;
+    if (tex_enabled && word) { uint64_t& w = cw[k]; if (word > w) w = word; }
+  }
   std::unordered_map<int, Pose> submap_pose;
   bool in_bounds(int i, int j, int k) const {
     int h = N / 2, hz = Nz / 2;
@@ -965,7 +976,18 @@ void* orc_octo_create(const OctoCfg* c) {
   return m;
 }
 void orc_octo_destroy(void* h) { delete (Octo*)h; }
-void orc_octo_reset(void* h) { ((Octo*)h)->cnt.clear(); }  // root.deactivate_all() taichi_octomap.py:210-211
+void orc_octo_reset(void* h) { ((Octo*)h)->cnt.clear(); ((Octo*)h)->cw.clear(); }  // root.deactivate_all() taichi_octomap.py:210-211
+void orc_octo_set_color(void* h, int enabled, int same_proj, double fx, double fy, double cx, double cy) {
+  Octo* m = (Octo*)h;
+  m->tex_enabled = enabled != 0; m->color_same_proj = same_proj != 0;
+  m->fxc = (float)fx; m->fyc = (float)fy; m->cxc = (float)cx; m->cyc = (float)cy;
+}
+static inline uint64_t octo_word(uint32_t seq, const uint8_t* p) {  // "Stupid OpenCV is BGR" (:121-124)
+  return ((uint64_t)seq << 24) | ((uint64_t)p[2] << 16) | ((uint64_t)p[1] << 8) | (uint64_t)p[0];
+}
+static inline void octo_rgb(uint64_t w, float* out) {
+  out[0] = (float)((w >> 16) & 255) / 255.0f; out[1] = (float)((w >> 8) & 255) / 255.0f; out[2] = (float)(w & 255) / 255.0f;
+}
 void orc_octo_set_submap_pose(void* h, int s, const float* R9, const float* T3) {
   Octo* m = (Octo*)h;
   Pose p; memcpy(p.R, R9, sizeof(p.R)); memcpy(p.T, T3, sizeof(p.T));
@@ -973,9 +995,14 @@ void orc_octo_set_submap_pose(void* h, int s, const float* R9, const float* T3) 
 }
 
 // recast_pcl_to_map_kernel + process_point  (taichi_octomap.py:134-145, :116-119)
+void orc_octo_integrate_points_rgb(void* h, const float* xyz, const uint8_t* rgb, int n, const float* R9, const float* T3, int submap);
 void orc_octo_integrate_points(void* h, const float* xyz, int n, const float* R9, const float* T3, int submap) {
+  orc_octo_integrate_points_rgb(h, xyz, nullptr, n, R9, T3, submap);
+}
+void orc_octo_integrate_points_rgb(void* h, const float* xyz, const uint8_t* rgb, int n, const float* R9, const float* T3, int submap) {
   Octo* m = (Octo*)h;
   const float vs = m->vs;
+  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;
   for (int idx = 0; idx < n; idx++) {
     float pt[3] = {xyz[3 * idx], xyz[3 * idx + 1], xyz[3 * idx + 2]};
     float p[3];
@@ -983,14 +1010,21 @@ void orc_octo_integrate_points(void* h, const float* xyz, int n, const float* R9
     p[0] += T3[0]; p[1] += T3[1]; p[2] += T3[2];                         // :141
     int i = iround(p[0] / vs), j = iround(p[1] / vs), k = iround(p[2] / vs);  // xyz_to_sijk mapping_common.py:251-255
     if (!m->in_bounds(i, j, k)) continue;
-    m->cnt[Key{submap, i, j, k}] += 1;                                    // :119
+    m->hit(Key{submap, i, j, k}, 1, rgb ? octo_word(m->frame_seq, rgb + 3 * (size_t)idx) : 0);  // :119-124
   }
 }
 
 // recast_depth_to_map_kernel  (taichi_octomap.py:147-169)
+void orc_octo_integrate_depth_tex(void* h, const uint16_t* depth, const uint8_t* tex, int TH, int TW, int H, int Wd, const float* R9,
+                                  const float* T3, int submap);
 void orc_octo_integrate_depth(void* h, const uint16_t* depth, int H, int Wd, const float* R9, const float* T3, int submap) {
+  orc_octo_integrate_depth_tex(h, depth, nullptr, 0, 0, H, Wd, R9, T3, submap);
+}
+void orc_octo_integrate_depth_tex(void* h, const uint16_t* depth, const uint8_t* tex, int TH, int TW, int H, int Wd, const float* R9,
+                                  const float* T3, int submap) {
   Octo* m = (Octo*)h;
   const float vs = m->vs;
+  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;
   const int step = m->step;
   const int hh = (int)((double)H / step), ww = (int)((double)Wd / step);
   const float fx = (float)m->fx, fy = (float)m->fy, cx = (float)m->cx, cy = (float)m->cy;
@@ -1008,7 +1042,18 @@ void orc_octo_integrate_depth(void* h, const uint16_t* depth, int H, int Wd, con
       p[0] += T3[0]; p[1] += T3[1]; p[2] += T3[2];                   // :159
       int vi = iround(p[0] / vs), vj = iround(p[1] / vs), vk = iround(p[2] / vs);
       if (!m->in_bounds(vi, vj, vk)) continue;
-      m->cnt[Key{submap, vi, vj, vk}] += 1;
+      uint64_t word = 0;
+      if (m->tex_enabled && tex) {  // :160-167
+        int tj = j, ti = i;
+        if (!m->color_same_proj) {  // color_ind_from_depth_pt (mapping_common.py:43-58), see orc_tsdf_integrate_depth_tex
+          ti = (int)((((float)i - cx) / fx) * m->fxc + m->cxc);
+          tj = (int)((((float)j - cy) / fy) * m->fyc + m->cyc);
+          if (ti < 0 || ti >= TH || tj < 0 || tj >= TW || tj >= TH || ti >= TW) { ti = 0; tj = 0; }
+        }
+        const uint8_t zero3[3] = {0, 0, 0};
+        word = octo_word(m->frame_seq, (tj < TH && ti < TW) ? tex + ((size_t)tj * TW + ti) * 3 : zero3);
+      }
+      m->hit(Key{submap, vi, vj, vk}, 1, word);
     }
   }
 }
@@ -1025,13 +1070,29 @@ int64_t orc_octo_gather(void* h, int submap, int64_t cap, int32_t* idx, uint32_t
   return n;
 }
 
+// colours of the rows of orc_octo_gather, same order
+void orc_octo_gather_color(void* h, int submap, int64_t cap, float* col) {
+  Octo* m = (Octo*)h;
+  int64_t n = 0;
+  for (auto& kv : m->cnt) {
+    if (kv.first.s != submap) continue;
+    if (n < cap) {
+      auto it = m->cw.find(kv.first);
+      octo_rgb(it == m->cw.end() ? 0 : it->second, col + 3 * n);
+    }
+    n++;
+  }
+}
+
 // cvt_occupy_to_voxels(level)  (taichi_octomap.py:90-102).  occupy.parent(level)
 // iterates the ACTIVE cells of the ancestor `level` levels above the leaf field:
 // level 1 = individual voxels, level L = K^(L-1)-aligned groups, reported at the
 // group's base coordinate; is_occupy is evaluated AT that base coordinate
 // (:97, :86-88: occupy > min_occupy_thres), so a group whose corner voxel was
 // never hit is not exported.  xyz = sijk_to_xyz (mapping_common.py:234-238).
-int64_t orc_octo_export(void* h, int submap, int level, int64_t cap, float* xyz) {
+int64_t orc_octo_export2(void* h, int submap, int level, int64_t cap, float* xyz, float* rgb);
+int64_t orc_octo_export(void* h, int submap, int level, int64_t cap, float* xyz) { return orc_octo_export2(h, submap, level, cap, xyz, nullptr); }
+int64_t orc_octo_export2(void* h, int submap, int level, int64_t cap, float* xyz, float* rgb) {
   Octo* m = (Octo*)h;
   const float vs = m->vs;
   int g = 1;
@@ -1055,6 +1116,10 @@ int64_t orc_octo_export(void* h, int submap, int level, int64_t cap, float* xyz)
       float p[3];
       rot(P.R, l, p);
       xyz[3 * n] = p[0] + P.T[0]; xyz[3 * n + 1] = p[1] + P.T[1]; xyz[3 * n + 2] = p[2] + P.T[2];
+      if (rgb && m->tex_enabled) {  // export_color[index] = color[sijk] (:101-102)
+        auto ic = m->cw.find(kv.first);
+        octo_rgb(ic == m->cw.end() ? 0 : ic->second, rgb + 3 * n);
+      }
     }
     n++;
   }
@@ -1066,6 +1131,7 @@ void orc_octo_fuse(void* hdst, void* hsrc) {
   Octo* D = (Octo*)hdst;
   Octo* S = (Octo*)hsrc;
   D->cnt.clear();
+  D->cw.clear();
   const float vs = D->vs;
   for (auto& kv : S->cnt) {
     float occ = (float)kv.second;
@@ -1076,7 +1142,9 @@ void orc_octo_fuse(void* hdst, void* hsrc) {
     rot(P.R, l, r);
     int i = iround((r[0] + P.T[0]) / vs), j = iround((r[1] + P.T[1]) / vs), k = iround((r[2] + P.T[2]) / vs);  // :182-183
     if (!D->in_bounds(i, j, k)) continue;
-    D->cnt[Key{0, i, j, k}] += kv.second;  // :186
+    uint64_t word = 0;  // color[ijk_] = submap_color[s,i,j,k] (:189), racing: the most recently integrated source colour wins
+    if (D->tex_enabled && S->tex_enabled) { auto ic = S->cw.find(kv.first); if (ic != S->cw.end()) word = ic->second; }
+    D->hit(Key{0, i, j, k}, kv.second, word);  // :186
   }
 }
 

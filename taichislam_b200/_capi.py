@@ -42,7 +42,7 @@ class OctoConfig(C.Structure):
                 ("recast_step", C.c_int32),
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
                 ("min_occupy_thres", C.c_int32), ("max_submaps", C.c_int32), ("max_blocks", C.c_int32),
-                ("max_image_pixels", C.c_int32), ("max_points", C.c_int32)]
+                ("max_image_pixels", C.c_int32), ("max_points", C.c_int32), ("texture_enabled", C.c_int32)]
 
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -108,6 +108,11 @@ SIGNATURES = {
     "tslam_octo_gather": (C.c_int, [_vp, _i32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),
     "tslam_octo_extract": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp]),
     "tslam_octo_fuse": (C.c_int, [_vp, _vp, _vp]),
+    "tslam_octo_set_color_intrinsics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "tslam_octo_integrate_points_rgb": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32, _vp, _vp, _i32, _vp]),
+    "tslam_octo_integrate_depth_tex": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "tslam_octo_gather2": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "tslam_octo_extract2": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "tslam_octo_sync": (C.c_int, [_vp, _vp]),
     "tslam_octo_launch_count": (_i64, [_vp]),
 }

@@ -260,6 +260,7 @@ struct OcGrid {
   int* n_blocks;
   unsigned long long* block_key;
   unsigned int* cnt;  // [max_blocks*512]
+  unsigned long long* cw;  // texture_enabled: [max_blocks*512] colour word (integrate seq << 24 | r << 16 | g << 8 | b), atomicMax
   int* err;
   int hN, hNz, N, Nz;
 };
@@ -273,12 +274,28 @@ struct tslam_octo {
   size_t table_cap;
   uint16_t* depth_stage;
   float* points_stage;
+  uint8_t* tex_stage;     // texture_enabled: device staging of a host colour image / point colours
+  unsigned int frame_seq; // integrate calls so far (saturates at 2^22-1)
   float* pose_R;
   float* pose_T;
   int* scratch_i;
   long long launches;
   int sm_count;
 };
+
+// colour pixel of depth pixel (i, j): texture[j, i] (color_same_proj) or color_ind_from_depth_pt
+// (mapping_common.py:43-58).  The reference tests color_i against h and color_j against w (swapped, :56); what passes
+// that test but lies outside the image is an out-of-bounds read there - pixel (0,0) here.  Returns false when even the
+// same-projection pixel is outside the colour image.
+__device__ __forceinline__ bool ts_color_pixel(const TsIntrin& in, int i, int j, int th, int tw, int& ti, int& tj) {
+  tj = j; ti = i;
+  if (!in.same_proj) {
+    ti = (int)((((float)i - in.cx) / in.fx) * in.fxc + in.cxc);
+    tj = (int)((((float)j - in.cy) / in.fy) * in.fyc + in.cyc);
+    if (ti < 0 || ti >= th || tj < 0 || tj >= tw || tj >= th || ti >= tw) { ti = 0; tj = 0; }
+  }
+  return tj < th && ti < tw;
+}
 
 // error plumbing (tslam_tsdf.cu)
 void ts_set_error(const char* fmt, ...);

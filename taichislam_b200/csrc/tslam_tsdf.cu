@@ -196,15 +196,8 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
       py = (fr.R[3] * x + fr.R[4] * y) + fr.R[5] * dep;
       pz = (fr.R[6] * x + fr.R[7] * y) + fr.R[8] * dep;
       if (tex) {
-        int tj = j, ti = i;  // color_same_proj: texture[j, i] (:206)
-        if (!in.same_proj) {  // color_ind_from_depth_pt (mapping_common.py:43-58, called at :209)
-          ti = (int)((((float)i - in.cx) / in.fx) * in.fxc + in.cxc);
-          tj = (int)((((float)j - in.cy) / in.fy) * in.fyc + in.cyc);
-          // the reference tests color_i against h and color_j against w (swapped, :56); what passes that test but lies
-          // outside the image is an out-of-bounds read there - here pixel (0,0) too
-          if (ti < 0 || ti >= th || tj < 0 || tj >= tw || tj >= th || ti >= tw) { ti = 0; tj = 0; }
-        }
-        if (tj < th && ti < tw) {
+        int tj, ti;  // texture[j, i] (:206) or color_ind_from_depth_pt (:209)
+        if (ts_color_pixel(in, i, j, th, tw, ti, tj)) {
           const uint8_t* p = tex + ((size_t)f * th * tw + (size_t)tj * tw + ti) * 3;
           cr = p[0]; cg = p[1]; cb = p[2];
         }

@@ -40,10 +40,12 @@ class Octomap(BaseMap):
         self.is_global_map = is_global_map
         self.recast_step = recast_step
         self.color_same_proj = color_same_proj
-        self.color = None
+        self.color = None  # the colour plane lives inside the library handle (:77-79); read it with _h.gather(color=True)
         self._h = OctoHandle(self.N, self.Nz, K=K, voxel_scale=ctor_voxel_scale, min_occupy_thres=min_occupy_thres,
                              min_ray_length=min_ray_length, max_ray_length=max_ray_length, recast_step=recast_step,
-                             max_submaps=min(max_submap_num, 1024), max_blocks=max_blocks)
+                             max_submaps=min(max_submap_num, 1024), max_blocks=max_blocks, texture_enabled=texture_enabled)
+        if texture_enabled:
+            self._h.set_color_intrinsics([1, 0, 0, 0, 1, 0, 0, 0, 1], color_same_proj)
         dev = torch.device("cuda", torch.cuda.current_device())
         n = max_disp_particles
         self.num_export_particles = Field(torch.zeros(1, dtype=torch.int32, device=dev))
@@ -67,6 +69,10 @@ class Octomap(BaseMap):
     def _on_intrinsics(self):
         self._h.set_intrinsics(self.K_cam_dep)
 
+    def set_color_camera_intrinsic(self, K):
+        super(Octomap, self).set_color_camera_intrinsic(K)
+        self._h.set_color_intrinsics(self.K_cam_color, self.color_same_proj)
+
     def _upload_submap_pose(self, submap_id, R, T):
         self._h.set_submap_pose(submap_id, R, T)
 
@@ -74,21 +80,28 @@ class Octomap(BaseMap):
     def recast_pcl_to_map(self, R, T, xyz_array, rgb_array, n=None):
         self.set_pose(R, T)
         xyz = np.ascontiguousarray(np.asarray(xyz_array, dtype=np.float32).reshape(-1, 3))
+        rgb = None
+        if self.enable_texture:  # :142-143 process_point(pt, rgb_array[index]); BGR -> RGB inside (:120-124)
+            rgb = np.ascontiguousarray(np.asarray(rgb_array, dtype=np.uint8).reshape(-1, 3))
         if n is not None:
             xyz = xyz[:n]
-        self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=self._active())
+            rgb = rgb[:n] if rgb is not None else None
+        self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=self._active(), rgb=rgb)
 
     def recast_depth_to_map(self, R, T, depthmap, texture):
         self.set_pose(R, T)
-        self._h.integrate_depth(np.asarray(depthmap), self.input_R_np, self.input_T_np, submap=self._active())
+        tex = np.ascontiguousarray(texture, dtype=np.uint8) if self.enable_texture else None  # :160-167
+        self._h.integrate_depth(np.asarray(depthmap), self.input_R_np, self.input_T_np, submap=self._active(), texture=tex)
 
     # :90-114
     def cvt_occupy_to_voxels(self, level):
         self.num_export_particles.t.zero_()
-        self._h.extract(self._active(), level, self.export_x.t, self.num_export_particles.t)
+        self._h.extract(self._active(), level, self.export_x.t, self.num_export_particles.t,
+                        self.export_color.t if self.enable_texture else None)  # :101-102
 
     def cvt_occupy_voxels_to(self, level, cur_num, max_disp_particles, x, color):
-        self._h.extract(self._active(), level, x.t[:max_disp_particles], cur_num.t)
+        self._h.extract(self._active(), level, x.t[:max_disp_particles], cur_num.t,
+                        color.t[:max_disp_particles] if self.enable_texture else None)  # :113-114
 
     def get_occupy_voxels(self, l):
         self.cvt_occupy_to_voxels(l)

@@ -140,18 +140,25 @@ def test_color_roundtrip_surface_and_mesh():
     o2.scatter(0, gi, gt, gw, gocc)
     o2.scatter_color(0, gi, gc)
     compare_colors(g2, o2)
+    # A vertex colour depends on the EDGE it was made on, not only on its position (a snapped vertex takes the colour of
+    # the edge's first corner, mu = 0), and neighbouring cells emit coincident degenerate triangles: match triangles on
+    # positions AND colours (18-D), both directions.
+    def same_coloured_mesh(gv, gcol, ov, ocol):
+        a = np.concatenate([gv.reshape(-1, 9), gcol.reshape(-1, 9)], 1).astype(np.float64)
+        b = np.concatenate([ov.reshape(-1, 9), ocol.reshape(-1, 9)], 1).astype(np.float64)
+        assert a.shape == b.shape
+        d_ab, _ = cKDTree(b).query(a)
+        d_ba, _ = cKDTree(a).query(b)
+        assert d_ab.max() <= 1e-5 and d_ba.max() <= 1e-5, (d_ab.max(), d_ba.max())
+
     ng, gv, gn, gcol = g2.marching_cubes(1, 0.1, color=True)
     no, ov, on, ocol = o2.marching_cubes_color(1, 0.1)
-    assert ng == no
-    a, b = gv.reshape(-1, 9).astype(np.float64), ov.reshape(-1, 9).astype(np.float64)
-    dist, j = cKDTree(b).query(a)
-    assert dist.max() <= 1e-6
-    assert np.abs(gcol.reshape(-1, 9) - ocol.reshape(-1, 9)[j]).max() <= 1e-6
+    assert ng == no > 1000
+    same_coloured_mesh(gv, gcol, ov, ocol)
     ng2, gv2, gn2, gcol2 = g2.marching_cubes(2, 0.1, color=True)  # generic-step path
     no2, ov2, on2, ocol2 = o2.marching_cubes_color(2, 0.1)
     assert ng2 == no2 > 100
-    dist, j = cKDTree(ov2.reshape(-1, 9).astype(np.float64)).query(gv2.reshape(-1, 9).astype(np.float64))
-    assert dist.max() <= 1e-6 and np.abs(gcol2.reshape(-1, 9) - ocol2.reshape(-1, 9)[j]).max() <= 1e-6
+    same_coloured_mesh(gv2, gcol2, ov2, ocol2)
 
 
 def test_textured_fusion():
@@ -230,3 +237,93 @@ def test_untextured_map_rejects_texture():
     g = TsdfHandle(256, 256, K=syn.K_DEPTH, is_global_map=True)
     with pytest.raises(Exception):
         g.integrate_depth(syn.scene_plane(3.0), np.eye(3)[None], np.zeros((1, 3)), texture=make_texture(0)[None])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Octomap colours (taichi_octomap.py:77-79, :120-124, :160-167, :189): latest integrate call wins, inside a call the
+# largest packed RGB (after the BGR->RGB swap).  8-bit channels / 255 on both sides -> exact comparison.
+# ---------------------------------------------------------------------------------------------------------------
+def octo_pair(map_scale, same_proj=True, Kcolor=None, **kw):
+    from oracle.oracle import OracleOctomap
+    from taichislam_b200.octo_handle import OctoHandle
+    o = OracleOctomap(map_scale=map_scale, voxel_scale=0.05, Kcam=syn.K_DEPTH, **kw)
+    o.set_color(True, same_proj, Kcolor)
+    g = OctoHandle(o.N, o.Nz, voxel_scale=0.05, Kcam=syn.K_DEPTH, max_submaps=8, texture_enabled=True, **kw)
+    g.set_color_intrinsics(Kcolor if Kcolor is not None else [1, 0, 0, 0, 1, 0, 0, 0, 1], same_proj)
+    return g, o
+
+
+def octo_equal(g, o, submap=0):
+    gi, gc, gcol = g.gather(submap, color=True)
+    oi, oc = o.gather(submap)
+    ocol = o.gather_color(submap)
+    kg, ko = key_sort(gi), key_sort(oi)
+    assert np.array_equal(gi[kg], oi[ko]) and np.array_equal(gc[kg], oc[ko])
+    assert np.array_equal(gcol[kg], ocol[ko])
+    assert (ocol > 0).any()
+
+
+def test_octomap_colors_points_depth_fusion():
+    rng = np.random.default_rng(11)
+    g, o = octo_pair([12.8, 12.8], K=2, min_occupy_thres=1, max_ray_length=5.0)
+    # clustered cloud: many points per voxel race for the colour; two calls: the later one wins where it hits
+    cl = (rng.normal(size=(40000, 3)) * 0.3 + np.array([1.0, 0.5, 0.5])).astype(np.float32)
+    for q in range(2):
+        rgb = rng.integers(0, 256, (len(cl), 3)).astype(np.uint8)
+        R, T = rot_xyz(0.1 * q, 0.05, -0.2), np.array([0.1, -0.2 * q, 0.05])
+        g.set_submap_pose(0, np.eye(3), np.zeros(3))
+        o.set_submap_pose(0, np.eye(3), np.zeros(3))
+        g.integrate_points(cl, R, T, rgb=rgb)
+        o.integrate_points_rgb(R, T, cl, rgb)
+    octo_equal(g, o)
+    # depth + colour image into submaps 1 and 2, same-projection and colour-camera variants
+    d = syn.scene_room()
+    for s in (1, 2):
+        R, T = rot_xyz(0.0, 0.1 * s, 0.2), np.array([0.1 * s, 0.0, 0.1])
+        g.set_submap_pose(s, rot_xyz(0.1, 0.0, 0.1 * s), np.array([0.5, 0.1 * s, 0.0]))  # pose rows start at zero
+        o.set_submap_pose(s, rot_xyz(0.1, 0.0, 0.1 * s), np.array([0.5, 0.1 * s, 0.0]))
+        tex = make_texture(40 + s)
+        g.integrate_depth(d, R, T, submap=s, texture=tex)
+        o.integrate_depth_tex(R, T, d, tex, submap=s)
+        octo_equal(g, o, s)
+    for level in (1, 2):
+        ng, xg, cg = g.export(level, submap=1, color=True)
+        no, xo, co = o.export_color(level, submap=1)
+        assert ng == no > 100
+        a, b = np.lexsort(xg.T[::-1]), np.lexsort(xo.T[::-1])
+        assert np.array_equal(xg[a], xo[b]) and np.array_equal(cg[a], co[b])
+    # fusion into a textured global map: counts add, colour = most recently integrated source voxel
+    gg, og = octo_pair([25.6, 25.6], K=2, min_occupy_thres=1)
+    for s in range(3):
+        Rs, Ts = rot_xyz(0.05 * s, 0.0, 0.3 * s), np.array([0.3 * s, -0.2 * s, 0.0])
+        gg.set_submap_pose(s, Rs, Ts)
+        og.set_submap_pose(s, Rs, Ts)
+    gg.fuse_from(g)
+    og.fuse_from(o)
+    octo_equal(gg, og)
+
+
+def test_octomap_color_camera_and_class():
+    th, tw = 240, 320
+    Kc = [s * 0.5 for s in syn.K_DEPTH]
+    Kc[8] = 1.0
+    g, o = octo_pair([12.8, 12.8], same_proj=False, Kcolor=Kc, K=2, min_occupy_thres=1, max_ray_length=5.0)
+    d, tex = syn.scene_sphere(3.0), make_texture(50, th, tw)
+    g.integrate_depth(d, np.eye(3), np.zeros(3), texture=tex)
+    o.integrate_depth_tex(np.eye(3), np.zeros(3), d, tex)
+    octo_equal(g, o)
+    # reference class surface
+    from taichislam_b200.mapping import Octomap
+    m = Octomap(map_scale=[12.8, 12.8], voxel_scale=0.05, min_occupy_thres=0, texture_enabled=True, max_ray_length=5.0,
+                max_disp_particles=200000)
+    m.set_dep_camera_intrinsic(np.array(syn.K_DEPTH).reshape(3, 3))
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    tex2 = make_texture(51)
+    m.recast_depth_to_map(np.eye(3), np.zeros(3), d, tex2)
+    x, c = m.get_occupy_voxels(1)
+    n = int(m.num_export_particles[None])
+    assert n > 1000
+    # exported colours are texture colours with the channels swapped (BGR -> RGB)
+    got = set(map(tuple, np.round(c[:n] * 255).astype(np.int32)))
+    have = set(map(tuple, tex2.reshape(-1, 3)[:, ::-1].astype(np.int32)))
+    assert got <= have

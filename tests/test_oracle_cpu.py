@@ -267,3 +267,24 @@ def test_texture_known_answers():
     assert n > 0 and set(map(tuple, np.unique(rgb, axis=0))) <= set(map(tuple, np.unique(col2, axis=0)))
     nt, v, nrm, c = m.marching_cubes_color(1, 0.1)
     assert nt > 1000 and c.min() >= 0.0 and c.max() <= 1.0 and (c[:, 1] > 0).all()
+
+
+def test_octomap_texture_known_answers():
+    """Octomap colour rule (taichi_octomap.py:120-124): BGR -> RGB swap, /255, later integrate call wins."""
+    o = OracleOctomap(map_scale=[12.8, 12.8], voxel_scale=0.05, K=2, min_occupy_thres=0)
+    o.set_color(True, True)
+    o.set_submap_pose(0, np.eye(3), np.zeros(3))
+    pts = np.array([[1.0, 1.0, 1.0], [1.0, 1.0, 1.0], [2.0, 0.5, 0.25]], np.float32)
+    rgb = np.array([[10, 20, 30], [200, 20, 30], [1, 2, 3]], np.uint8)
+    o.integrate_points_rgb(np.eye(3), np.zeros(3), pts, rgb)
+    idx, cnt = o.gather(0)
+    col = o.gather_color(0)
+    assert cnt.tolist() == [2, 1]
+    # voxel (20,20,20): two racing points -> the larger packed RGB-after-swap = (30,20,200) vs (30,20,10) -> first
+    assert np.allclose(col[list(map(tuple, idx)).index((20, 20, 20))] * 255, [30, 20, 200])
+    assert np.allclose(col[list(map(tuple, idx)).index((40, 10, 5))] * 255, [3, 2, 1])
+    o.integrate_points_rgb(np.eye(3), np.zeros(3), pts[:1], np.array([[0, 0, 1]], np.uint8))  # later call wins, even if "smaller"
+    col = o.gather_color(0)
+    assert np.allclose(col[list(map(tuple, o.gather(0)[0])).index((20, 20, 20))] * 255, [1, 0, 0])
+    n, xyz, c = o.export_color(1)
+    assert n == 2 and np.allclose(np.sort(c[:, 0] * 255), [1, 3])

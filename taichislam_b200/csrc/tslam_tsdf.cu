@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
 #define RM_WIN 16
 #define RM_WIN3 4096
 #define RM_FIX 16777216.0f   // 2^24
+#define RM_WIN_STEPS 18      // a sample >= 18 voxels from the sensor origin lies outside the +-8 voxel window on some axis
 #define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
 #define RM_SMEM (RM_WIN3 * 16 + RM_TAB * 8)
 #define RM_SMEM_TEX (RM_SMEM + RM_WIN3 * 8)  // textured maps: + one 64-bit colour word per window voxel
@@ -381,35 +382,51 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
     }
     const int wq = __float2int_rn(wgt * RM_FIX);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
+    // voxel of the previous far-field sample: a new block is looked up only when a coordinate leaves its 16-cell
+    // (bits >= 4 differ).  Starts at the occupy voxel's block (cur_blk), or at a value no in-bounds voxel shares.
+    int pxi = 0x40000000, pyi = 0x40000000, pzi = 0x40000000;
+    if (cur_blk >= 0) {
+      int ks, kx, ky, kz;
+      ts_unpack_key(cur_key, ks, kx, ky, kz);
+      pxi = kx << TS_BSHIFT; pyi = ky << TS_BSHIFT; pzi = kz << TS_BSHIFT;
+    }
+    const unsigned uN = (unsigned)g.N, uNz = (unsigned)g.Nz;
     float jf = 0.0f;
-    for (int it = 0; it < nmax; ++it) {
+    // One step of the march (:252-267).  WIN: the sample may fall into the shared-memory window (only the first
+    // RM_WIN_STEPS steps can: the window reaches 8 voxels from the sensor origin).
+    auto step = [&](const int it, const bool WIN) __attribute__((always_inline)) {
       jf += 1.0f;  // :252
       const float x = (ux * jf) * vs + Tx, y = (uy * jf) * vs + Ty, z = (uz * jf) * vs + Tz;  // :253
       const int xi = iroundf(div_vs(x, vs, rvs)), yi = iroundf(div_vs(y, vs, rvs)), zi = iroundf(div_vs(z, vs, rvs));  // :254
-      const float vx = Px - x, vy = Py - y, vz = Pz - z;                                      // :258
-      const float d = sqrtf((vx * vx + vy * vy) + vz * vz);                                  // :259
-      const float ds = d * sgnf((vx * mx + vy * my) + vz * mz);                              // :260
-      const float a = wgt * ds;                                                               // :264
+      // (ds = L - j*vs would be cheaper and equal up to ~1e-6 m, but it was measured to buy nothing - the kernel is
+      // bound by the reductions - and it moves marching-cubes topology where |TSDF| ~ 1e-6: the reference's formula stays.)
+      const float vx = Px - x, vy = Py - y, vz = Pz - z;                                       // :258
+      const float d = sqrtf((vx * vx + vy * vy) + vz * vz);                                     // :259
+      const float ds = d * sgnf((vx * mx + vy * my) + vz * mz);                                 // :260
+      const float a = wgt * ds;                                                                 // :264
       const bool stepping = it < n;
-      const bool inb = stepping && ts_in_bounds(g, xi, yi, zi);
+      const bool inb = stepping && (unsigned)(xi + g.hN) < uN && (unsigned)(yi + g.hN) < uN && (unsigned)(zi + g.hNz) < uNz;
       my_oob += (stepping && !inb) ? 1u : 0u;
-      const unsigned dx = (unsigned)(xi - wx), dy = (unsigned)(yi - wy), dz = (unsigned)(zi - wz);
-      const bool in_win = inb && win_ok && dx < RM_WIN && dy < RM_WIN && dz < RM_WIN && fabsf(a) < 120.0f;
-      if (in_win) {  // near field: exact fixed-point sums in shared memory
-        const int e = (int)((dx << 8) | (dy << 4) | dz);
-        win_add(&w_alo[e], &w_ahi[e], __float2int_rn(a * RM_FIX));
-        win_add(&w_blo[e], &w_bhi[e], wq);
-        if (TEX) {
-          const int cl = min(4095, (int)(fabsf(ds) / vs * 16.0f));
-          atomicMax(&w_cw[e], cw_hi | ((unsigned long long)(4095 - cl) << 30));
+      bool far = inb;
+      if (WIN) {
+        const unsigned dx = (unsigned)(xi - wx), dy = (unsigned)(yi - wy), dz = (unsigned)(zi - wz);
+        const bool in_win = inb && win_ok && dx < RM_WIN && dy < RM_WIN && dz < RM_WIN && fabsf(a) < 120.0f;
+        if (in_win) {  // near field: exact fixed-point sums in shared memory
+          const int e = (int)((dx << 8) | (dy << 4) | dz);
+          win_add(&w_alo[e], &w_ahi[e], __float2int_rn(a * RM_FIX));
+          win_add(&w_blo[e], &w_bhi[e], wq);
+          if (TEX) {
+            const int cl = min(4095, (int)(fabsf(ds) / vs * 16.0f));
+            atomicMax(&w_cw[e], cw_hi | ((unsigned long long)(4095 - cl) << 30));
+          }
+          my_updates++;
         }
-        my_updates++;
+        far = inb && !in_win;
       }
-      const bool far = inb && !in_win;
-      const unsigned long long key = ts_pack_key(s, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
-      if (far && key != cur_key) {  // block boundary crossed: ~ every 10th step of a lane
-        cur_key = key;
-        cur_blk = rm_lookup(g, btab, key, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT);
+      if (far && ((((xi ^ pxi) | (yi ^ pyi) | (zi ^ pzi)) >> TS_BSHIFT) != 0)) {  // block boundary crossed: ~ every 10th step of a lane
+        pxi = xi; pyi = yi; pzi = zi;
+        cur_blk = rm_lookup(g, btab, ts_pack_key(s, xi >> TS_BSHIFT, yi >> TS_BSHIFT, zi >> TS_BSHIFT), xi >> TS_BSHIFT, yi >> TS_BSHIFT,
+                            zi >> TS_BSHIFT);
       }
       __syncwarp();
       if (far && cur_blk >= 0) {  // cur_blk < 0: pool exhausted (error flag raised)
@@ -421,7 +438,12 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
         }
         my_updates++;
       }
-    }
+    };
+    const int n1 = min(nmax, RM_WIN_STEPS);
+    int it = 0;
+    for (; it < n1; ++it) step(it, true);
+#pragma unroll 2
+    for (; it < nmax; ++it) step(it, false);
     // flush the window: one reduction per touched voxel.  Pass 1 finds which of the <= 8 overlapped blocks hold
     // touched voxels, 8 threads resolve (activate) exactly those, pass 2 emits the reductions.
     __syncthreads();

@@ -93,8 +93,12 @@ int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, 
 /* Per-frame form of the same call, for callers that hand over one frame at a time (the reference API):
  * copies ONE host frame to a device staging slot on an internal copy stream (overlapping the kernels of the
  * previous batch) and records its pose; TSLAM_MAX_BATCH queued frames - or tslam_tsdf_flush, which every
- * reader calls implicitly - are integrated and committed with one launch triple.  Pinned host frames must
- * stay valid until the next flush; pageable ones may be reused immediately. */
+ * reader calls implicitly - are integrated and committed with one launch triple.  Pageable frames may be reused
+ * immediately.  PAGE-LOCKED (pinned / cudaHostRegister'ed) frames are not copied at all: the GPU fetches their
+ * sampled rows (every recast_step-th row) straight from host memory a few calls later - half the PCIe bytes for
+ * recast_step 2 - so they must stay valid and unchanged until tslam_tsdf_flush has returned and the stream has
+ * been synchronised, or until 2*TSLAM_MAX_BATCH further frames have been queued (the call blocks rather than
+ * letting the host run further ahead).  TSLAM_ZERO_COPY=0 in the environment restores whole-frame DMA copies. */
 int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
                            const float* T3, int32_t submap, void* stream);
 int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);

@@ -220,6 +220,17 @@ struct tslam_tsdf {
   uint8_t* rgb_stage;     // device staging for point-cloud colours
   unsigned int frame_seq; // frames integrated so far (saturates at 2^22-1)
   int q_th, q_tw, q_has_tex;
+  // pinned host frames are not copied: q_hptr[q] = their device alias; the sampled rows are fetched over PCIe by
+  // k_gather_rows in groups of TS_GATHER_GROUP frames (q_gathered = frames already handed to a gather launch)
+  const uint16_t* q_hptr[TSLAM_MAX_BATCH];
+  int q_gathered;
+  int zero_copy;  // 0 = off (TSLAM_ZERO_COPY=0)
+  int queue_launch;  // frames per queue launch (TSLAM_QUEUE_LAUNCH, default TSLAM_MAX_BATCH/2)
+  int trace;         // TSLAM_TRACE=1: print a per-launch timeline of the queue (debug)
+  cudaEvent_t tr_ev[2][4];  // per staging buffer: copy stream first op / last op, main stream launch begin / end
+  cudaEvent_t tr_base;
+  int tr_have[2];
+  int rm_reserve;    // SMs left out of the ray-march grid (2 once page-locked frames are being gathered, else 0)
   float* points_stage;    // device staging for host point clouds
   TsCounters* counters;
   float* pose_R;       // device pose table [max_submaps*9]

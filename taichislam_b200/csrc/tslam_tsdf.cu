@@ -796,7 +796,27 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
   TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
   TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)2 * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));  // double buffered
-  TS_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;  // highest priority: the gather kernel's few CTAs go first when SM slots free up
+    TS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TS_CUDA(cudaStreamCreateWithPriority(&m->copy_stream, cudaStreamNonBlocking, prio_hi));
+  }
+  {
+    const char* zc = getenv("TSLAM_ZERO_COPY");  // A/B switch: 0 = always DMA-copy whole frames
+    m->zero_copy = (zc && zc[0] == '0') ? 0 : 1;
+    // frames per queue launch: half a batch, so that the kernels of the first half run while the caller is still
+    // handing over the second half (a reader that flushes every TSLAM_MAX_BATCH frames waits for half the work)
+    m->trace = getenv("TSLAM_TRACE") != nullptr;
+    if (m->trace) {
+      for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 4; k++) TS_CUDA(cudaEventCreate(&m->tr_ev[i][k]));
+      TS_CUDA(cudaEventCreate(&m->tr_base));
+      TS_CUDA(cudaEventRecord(m->tr_base, 0));
+    }
+    const char* ql = getenv("TSLAM_QUEUE_LAUNCH");
+    m->queue_launch = ql ? atoi(ql) : TSLAM_MAX_BATCH / 2;
+    if (m->queue_launch < 1 || m->queue_launch > TSLAM_MAX_BATCH) m->queue_launch = TSLAM_MAX_BATCH;
+  }
   for (int i = 0; i < 2; i++) {
     TS_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
     TS_CUDA(cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
@@ -853,6 +873,7 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
   int nb = 0;
   m->n_integrate_calls = 0;  // pending sums are discarded with the blocks
   m->q_n = 0;                // ... and so are queued frames
+  m->q_gathered = 0;
   TS_CUDA(cudaMemcpyAsync(&nb, g.n_blocks, 4, cudaMemcpyDeviceToHost, st));
   TS_CUDA(cudaStreamSynchronize(st));
   if (nb > g.max_blocks) nb = g.max_blocks;
@@ -1016,8 +1037,8 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
       k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
                                                                      m->ray_list_cap, m->counters);
     else
-      k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                      m->ray_list_cap, m->counters);
+      k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                                     m->ray_list_cap, m->counters);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
     k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
@@ -1090,12 +1111,73 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
 // the previous batch) and records its pose; a full queue (TSLAM_MAX_BATCH frames) or tslam_tsdf_flush launches
 // the batch: bucket -> ray march -> commit.
 // ---------------------------------------------------------------------------
+// Pinned (page-locked) host frames: instead of a DMA copy of the whole 614 KB frame, a small kernel reads ONLY THE
+// SAMPLED ROWS (every recast_step-th row, :192) straight from host memory over PCIe - 16-byte loads, a warp covers
+// 512 contiguous bytes - and drops them at their place in the device staging frame.  Half the PCIe bytes for
+// recast_step 2, one launch per TS_GATHER_GROUP frames instead of one copy call per frame.
+#define TS_GATHER_GROUP 8
+struct TsGatherArgs {
+  const uint4* src[TS_GATHER_GROUP];
+  uint4* dst[TS_GATHER_GROUP];
+};
+__global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ TsGatherArgs ga, int hh, int row_u4, int row_stride_u4) {
+  const uint4* __restrict__ src = ga.src[blockIdx.y];
+  uint4* __restrict__ dst = ga.dst[blockIdx.y];
+  const int total = hh * row_u4;
+  const int base = (blockIdx.x * 256 + threadIdx.x) * 4;
+  uint4 v[4];
+  int off[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {  // 4 independent 16-byte PCIe reads in flight per thread
+    const int i = base + k;
+    off[k] = -1;
+    if (i < total) {
+      const int jj = i / row_u4, c = i - jj * row_u4;
+      off[k] = jj * row_stride_u4 + c;
+      v[k] = __ldcs(src + off[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (off[k] >= 0) dst[off[k]] = v[k];
+}
+
+// hand the queued zero-copy frames [q_gathered, q_n) to gather launches on the copy stream
+static int ts_gather_pending(tslam_tsdf* m) {
+  const int b = m->q_buf;
+  const int step = m->cfg.recast_step;
+  const int hh = (int)((double)m->q_h / step), row_u4 = m->q_w / 8;
+  while (m->q_gathered < m->q_n) {
+    TsGatherArgs ga;
+    int k = 0;
+    while (m->q_gathered < m->q_n && k < TS_GATHER_GROUP) {
+      const int q = m->q_gathered++;
+      if (!m->q_hptr[q]) continue;
+      ga.src[k] = (const uint4*)m->q_hptr[q];
+      ga.dst[k] = (uint4*)(m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * m->q_h * m->q_w);
+      k++;
+    }
+    if (k == 0 || hh <= 0) continue;
+    dim3 grid((hh * row_u4 + 1023) / 1024, k);
+    k_gather_rows<<<grid, 256, 0, m->copy_stream>>>(ga, hh, row_u4, step * row_u4);
+    TS_LAUNCH_CHECK(m);
+  }
+  return TSLAM_OK;
+}
+
 static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   const int n = m->q_n;
   if (n == 0) return TSLAM_OK;
   const int b = m->q_buf;
+  {
+    int rcg = ts_gather_pending(m);
+    if (rcg) return rcg;
+  }
+  m->q_gathered = 0;
+  if (m->trace) TS_CUDA(cudaEventRecord(m->tr_ev[b][1], m->copy_stream));
   TS_CUDA(cudaEventRecord(m->ev_copied[b], m->copy_stream));
   TS_CUDA(cudaStreamWaitEvent(st, m->ev_copied[b], 0));
+  if (m->trace) TS_CUDA(cudaEventRecord(m->tr_ev[b][2], st));
   const uint16_t* src = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels;
   m->q_n = 0;  // (integrate may recurse into flush through readers; the queue is empty from here on)
   m->q_buf = b ^ 1;
@@ -1105,6 +1187,7 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   if (rc) return rc;
   TS_CUDA(cudaEventRecord(m->ev_free[b], st));
   m->ev_free_valid[b] = true;
+  if (m->trace) { TS_CUDA(cudaEventRecord(m->tr_ev[b][3], st)); m->tr_have[b] = n; }
   return TSLAM_OK;
 }
 
@@ -1135,12 +1218,35 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
   if (q == 0) {
     m->q_h = h; m->q_w = w;
     m->q_has_tex = has_tex; m->q_th = th; m->q_tw = tw;
-    if (m->ev_free_valid[b]) TS_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_free[b], 0));  // kernels that read this buffer are done
+    // the kernels that read this staging buffer (two batches ago) must be done.  Waiting on the HOST bounds how far
+    // the caller can run ahead of the GPU: a pinned frame is consumed before 2*TSLAM_MAX_BATCH further frames are queued.
+    if (m->ev_free_valid[b]) TS_CUDA(cudaEventSynchronize(m->ev_free[b]));
+    m->q_gathered = 0;
+    if (m->trace) {
+      if (m->tr_have[b]) {  // timeline of the launch that used this buffer last (ms since handle creation)
+        float t[4];
+        for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], m->tr_base, m->tr_ev[b][k]);
+        fprintf(stderr, "[tslam trace] buf %d frames %d: copy %.3f..%.3f  kernels %.3f..%.3f ms\n", b, m->tr_have[b], t[0], t[1], t[2], t[3]);
+      }
+      TS_CUDA(cudaEventRecord(m->tr_ev[b][0], m->copy_stream));
+    }
   }
   // One linear copy of the whole frame.  (A strided 2-D copy of only the sampled rows halves the bytes but was
   // measured SLOWER from pinned memory: 30.2 k vs 36.5 k frames/s end to end - 240 row descriptors of 1280 B.)
   uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
-  TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  m->q_hptr[q] = nullptr;
+  if (m->zero_copy && m->cfg.recast_step >= 2 && (w % 8) == 0 && ((uintptr_t)depth_host % 16) == 0 && ((size_t)h * w % 8) == 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, depth_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      m->q_hptr[q] = (const uint16_t*)at.devicePointer;
+      // the persistent ray-march kernel owns every register of the SMs it runs on: keep two SMs out of its grid so
+      // that the row gather of the NEXT launch's frames can run (and keep PCIe busy) while it marches
+      if (m->sm_count > 8) m->rm_reserve = 2;
+    }
+    else
+      cudaGetLastError();
+  }
+  if (!m->q_hptr[q]) TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
   if (has_tex) {
     uint8_t* tdst = m->tex_stage + ((size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * th * tw) * 3;
     TS_CUDA(cudaMemcpyAsync(tdst, tex_host, (size_t)th * tw * 3, cudaMemcpyHostToDevice, m->copy_stream));
@@ -1149,7 +1255,8 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;
   m->q_n = q + 1;
-  if (m->q_n == TSLAM_MAX_BATCH) return ts_launch_queue(m, st);
+  if (m->q_n == m->queue_launch) return ts_launch_queue(m, st);
+  if (m->q_n - m->q_gathered >= TS_GATHER_GROUP) return ts_gather_pending(m);
   return TSLAM_OK;
 }
 

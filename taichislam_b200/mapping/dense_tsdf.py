@@ -7,6 +7,7 @@ queues the frame (pinned staging + pose) and frames are integrated in batches of
 launch; any reader (`count_active`, `to_numpy`, `cvt_*`, field reads, the mesher) flushes the
 queue first, so results are indistinguishable from per-frame execution.
 """
+import collections
 import math
 import time
 
@@ -62,6 +63,11 @@ class DenseTSDF(BaseMap):
         self._init_export_fields()
         self._queue = self._h.L.tslam_tsdf_queue_depth
         self._queue_tex = self._h.L.tslam_tsdf_queue_depth_tex
+        # page-locked frames are read by the GPU straight from host memory a few calls later (include/tslam.h): keep
+        # the arrays alive for as long as the library may still read them (it never runs more than 2 batches ahead)
+        self._frame_refs = collections.deque(maxlen=3 * capi.MAX_BATCH)
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        self._dev_index = torch.cuda.current_device()
         if texture_enabled:
             self._h.set_color_intrinsics([1, 0, 0, 0, 1, 0, 0, 0, 1], color_same_proj)
         self._pR, self._pT = self.input_R_np.ctypes.data, self.input_T_np.ctypes.data  # persistent pose buffers (BaseMap.set_pose)
@@ -104,6 +110,7 @@ class DenseTSDF(BaseMap):
             depthmap = np.ascontiguousarray(depthmap, dtype=np.uint16)
         h, w = depthmap.shape
         sid = 0 if self.is_global_map else self.active_submap_id.v
+        self._frame_refs.append(depthmap)
         if self.enable_texture:  # ti.static(self.enable_texture) (:205): the colour image rides along (uint8 [th,tw,3])
             if not self.color_same_proj and self.K_cam_color is None:
                 raise RuntimeError("set_color_camera_intrinsic() must be called before recast_depth_to_map (color_same_proj=False)")
@@ -120,6 +127,9 @@ class DenseTSDF(BaseMap):
             capi.check(rc)
 
     def _stream_ptr(self):
+        # raw handle of torch's current stream; the private accessor skips building a Stream object (once per frame)
+        if self._raw_stream is not None:
+            return self._raw_stream(self._dev_index)
         return self._torch.cuda.current_stream().cuda_stream
 
     def _flush(self):

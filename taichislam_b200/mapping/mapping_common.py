@@ -21,6 +21,7 @@ class BaseMap:
         self.base_R_np = np.eye(3)
         self.input_R_np = np.eye(3, dtype=np.float32)   # input_R / input_T 0-d fields (:12-13), kept on the host
         self.input_T_np = np.zeros(3, dtype=np.float32)
+        self._pose_tmp_R, self._pose_tmp_d, self._pose_tmp_T = np.zeros((3, 3)), np.zeros(3), np.zeros(3)
         self.frame_id = 0
         self.submap_enabled = False
         self.voxel_scale = voxel_scale
@@ -86,7 +87,19 @@ class BaseMap:
         self.base_R_np = np.asarray(_R, dtype=np.float64)
 
     def set_pose(self, _R, _T):  # :149-156
-        _R, _T = self.convert_by_base(_R, _T)
-        # f64 -> f32 cast into persistent buffers (their addresses are handed to the C ABI every frame)
-        np.copyto(self.input_R_np, _R, casting="same_kind")
-        np.copyto(self.input_T_np, _T, casting="same_kind")
+        # convert_by_base (:91-100) without temporaries - this runs once per frame: same f64 operations in the same
+        # order (R' = Rb^T R, T' = Rb^T (T - Tb)), results cast f64 -> f32 into the persistent buffers whose addresses are
+        # handed to the C ABI every frame
+        R = _R if (type(_R) is np.ndarray and _R.dtype == np.float64) else np.asarray(_R, dtype=np.float64)
+        T = _T if (type(_T) is np.ndarray and _T.dtype == np.float64) else np.asarray(_T, dtype=np.float64)
+        if self.submap_enabled:
+            sid = self.active_submap_id.v
+            Rb, Tb = self.submaps_base_R_np[sid], self.submaps_base_T_np[sid]
+        else:
+            Rb, Tb = self.base_R_np, self.base_T_np
+        Rbi = Rb.T
+        np.matmul(Rbi, R, out=self._pose_tmp_R)
+        np.subtract(T.reshape(3), Tb, out=self._pose_tmp_d)
+        np.matmul(Rbi, self._pose_tmp_d, out=self._pose_tmp_T)
+        self.input_R_np[...] = self._pose_tmp_R
+        self.input_T_np[...] = self._pose_tmp_T

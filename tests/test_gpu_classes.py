@@ -37,7 +37,7 @@ def test_dense_tsdf_per_frame_api_matches_oracle():
     # at ZERO: like the reference, poses are meaningless until the active submap's base pose is set.
     m.set_base_pose_submap(0, base_R, base_T)
     d = syn.scene_room()
-    n = 70  # crosses the 64-frame queue boundary
+    n = 70  # crosses the queue's launch boundaries (a launch every TSLAM_MAX_BATCH/2 = 32 frames)
     for q in range(n):
         R, T = syn.stream_pose(q)
         Rw, Tw = base_R @ R, base_R @ T + base_T
@@ -45,9 +45,9 @@ def test_dense_tsdf_per_frame_api_matches_oracle():
         # set_pose = convert_by_base in f64, then f32 (mapping_common.py:149-156)
         Ri = (base_R.T @ Rw).astype(np.float32)
         Ti = (base_R.T @ (Tw - base_T)).astype(np.float32)
-        # the class queues frames and commits once per launch of <= 64 frames; the oracle commits at the same points
+        # the class queues frames and commits once per launch of 32 frames; the oracle commits at the same points
         # (commit granularity only matters for voxels saturated at Wmax=1000, dense_tsdf.py:267 - see DESIGN.md)
-        o.integrate_depth(Ri, Ti, d, commit=(q == 63 or q == n - 1))
+        o.integrate_depth(Ri, Ti, d, commit=(q % 32 == 31 or q == n - 1))
     assert m.count_active() == o.count_active()
     num = m.count_active()
     idx = np.zeros((num, 3), np.int16); t = np.zeros(num, np.float16); w = np.zeros(num, np.float16); occ = np.zeros(num, np.int8)

@@ -48,6 +48,16 @@ def scene_room(seed=3, h=H, w=W):
     return d.astype(np.uint16)
 
 
+def texture_gradient(seed, h=H, w=W):
+    """Seeded synthetic colour image uint8 [h,w,3]: channel gradients + noise, channel 0 never 0 (marching cubes treats
+    r == 0 as "no colour", marching_cube_mesher.py:73-79)."""
+    rng = np.random.default_rng(seed)
+    jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    t = np.stack([(ii * 255 // max(w - 1, 1)), (jj * 255 // max(h - 1, 1)), ((ii + jj) % 256)], -1).astype(np.int32)
+    t = np.clip(t + rng.integers(-20, 21, t.shape), 1, 255)
+    return t.astype(np.uint8)
+
+
 def stream_pose(t, period=1000, radius=0.5):
     """Pose t of the bench stream: R = Rz(2*pi*t/period), T on a circle of `radius` m."""
     a = 2.0 * np.pi * t / period

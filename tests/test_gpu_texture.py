@@ -15,11 +15,7 @@ TOL = 1e-4
 
 
 def make_texture(seed, h=480, w=640):
-    rng = np.random.default_rng(seed)
-    jj, ii = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
-    t = np.stack([(ii * 255 // (w - 1)), (jj * 255 // (h - 1)), ((ii + jj) % 256)], -1).astype(np.int32)
-    t = np.clip(t + rng.integers(-20, 21, t.shape), 1, 255)  # channel 0 never 0: MC treats r == 0 as "no colour"
-    return t.astype(np.uint8)
+    return syn.texture_gradient(seed, h, w)
 
 
 def make_pair(map_scale, same_proj=True, Kcolor=None, **kw):

@@ -288,3 +288,29 @@ def test_octomap_texture_known_answers():
     assert np.allclose(col[list(map(tuple, o.gather(0)[0])).index((20, 20, 20))] * 255, [1, 0, 0])
     n, xyz, c = o.export_color(1)
     assert n == 2 and np.allclose(np.sort(c[:, 0] * 255), [1, 3])
+
+
+def test_golden_texture_vectors():
+    """The oracle's texture rule pinned by committed vectors (tools/make_golden.py): colours are 10-bit (TSDF) / 8-bit
+    (Octomap) quantised values, so the hashes are exact."""
+    g = GOLD["texture_256"]
+    o = OracleTSDF(map_scale=[12.8, 12.8], K=syn.K_DEPTH, is_global_map=True, disp_ceiling=5.0)
+    o.set_color(True, True)
+    for q in range(2):
+        R, T = syn.stream_pose(40 * q)
+        o.integrate_depth_tex(R, T, syn.scene_room(), syn.texture_gradient(100 + q), commit=True)
+    idx, t, w, occ = o.gather()
+    col = o.gather_color(0)
+    assert idx.shape[0] == g["active"] and sha(idx) == g["idx_sha256"] and sha(col) == g["color_sha256"]
+    assert int((col[:, 0] > 0).sum()) == g["coloured"]
+    nt, v, nrm, vc = o.marching_cubes_color(1, 0.1)
+    assert nt == g["mc_triangles"]
+    assert np.allclose(vc.astype(np.float64).sum(0), g["mc_color_sum"], rtol=1e-9)
+    go = GOLD["octomap_texture"]
+    oo = OracleOctomap(map_scale=[12.8, 12.8], voxel_scale=0.05, K=2, min_occupy_thres=1, Kcam=syn.K_DEPTH, max_ray_length=5.0)
+    oo.set_color(True, True)
+    oo.set_submap_pose(0, np.eye(3), np.zeros(3))
+    oo.integrate_depth_tex(np.eye(3), np.zeros(3), syn.scene_room(), syn.texture_gradient(102))
+    oi, oc = oo.gather(0)
+    assert oi.shape[0] == go["voxels"] and sha(oi) == go["idx_sha256"] and sha(oc) == go["count_sha256"]
+    assert sha(oo.gather_color(0)) == go["color_sha256"]

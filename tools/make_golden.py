@@ -76,6 +76,25 @@ def main():
                        "tsdf_sum": float(t_.astype(np.float64).sum()), "w_sum": float(w_.astype(np.float64).sum()),
                        "occ_sum": int(oc_.sum())}
     g["integrate_256"] = syn_g
+    # texture (canonical colour rule, DESIGN.md "Texture"): two textured frames, colours of the observed voxels in
+    # lexicographic voxel order; a coloured mesh; Octomap colours
+    o = OracleTSDF(map_scale=[12.8, 12.8], K=syn.K_DEPTH, is_global_map=True, disp_ceiling=5.0)
+    o.set_color(True, True)
+    for q in range(2):
+        R, T = syn.stream_pose(40 * q)
+        o.integrate_depth_tex(R, T, syn.scene_room(), syn.texture_gradient(100 + q), commit=True)
+    i_, t_, w_, oc_ = o.gather()
+    col = o.gather_color(0)
+    nt, v, nrm, vc = o.marching_cubes_color(1, 0.1)
+    g["texture_256"] = {"active": int(i_.shape[0]), "idx_sha256": sha(i_), "color_sha256": sha(col),
+                        "color_sum": [float(x) for x in col.astype(np.float64).sum(0)], "coloured": int((col[:, 0] > 0).sum()),
+                        "mc_triangles": int(nt), "mc_color_sum": [float(x) for x in vc.astype(np.float64).sum(0)]}
+    oo = OracleOctomap(map_scale=[12.8, 12.8], voxel_scale=0.05, K=2, min_occupy_thres=1, Kcam=syn.K_DEPTH, max_ray_length=5.0)
+    oo.set_color(True, True)
+    oo.set_submap_pose(0, np.eye(3), np.zeros(3))
+    oo.integrate_depth_tex(np.eye(3), np.zeros(3), syn.scene_room(), syn.texture_gradient(102))
+    oi, ocnt = oo.gather(0)
+    g["octomap_texture"] = {"voxels": int(oi.shape[0]), "idx_sha256": sha(oi), "count_sha256": sha(ocnt), "color_sha256": sha(oo.gather_color(0))}
     oc = OracleOctomap(map_scale=[51.2, 51.2], voxel_scale=0.05, K=2, min_occupy_thres=2)
     oc.integrate_points(np.eye(3), np.zeros(3), syn.octo_cloud(100000, seed=1))
     oi, ocnt = oc.gather()

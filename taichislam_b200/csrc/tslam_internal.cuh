@@ -225,7 +225,8 @@ struct tslam_tsdf {
   const uint16_t* q_hptr[TSLAM_MAX_BATCH];
   int q_gathered;
   int zero_copy;  // 0 = off (TSLAM_ZERO_COPY=0)
-  int queue_launch;  // frames per queue launch (TSLAM_QUEUE_LAUNCH, default TSLAM_MAX_BATCH/2)
+  int queue_launch[2];  // frames per queue launch, alternating (TSLAM_QUEUE_LAUNCH="a,b", default 32,32)
+  int q_phase;          // which of the two thresholds the current launch uses (back to 0 at every flush)
   int trace;         // TSLAM_TRACE=1: print a per-launch timeline of the queue (debug)
   cudaEvent_t tr_ev[2][4];  // per staging buffer: copy stream first op / last op, main stream launch begin / end
   cudaEvent_t tr_base;

@@ -804,8 +804,6 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   {
     const char* zc = getenv("TSLAM_ZERO_COPY");  // A/B switch: 0 = always DMA-copy whole frames
     m->zero_copy = (zc && zc[0] == '0') ? 0 : 1;
-    // frames per queue launch: half a batch, so that the kernels of the first half run while the caller is still
-    // handing over the second half (a reader that flushes every TSLAM_MAX_BATCH frames waits for half the work)
     m->trace = getenv("TSLAM_TRACE") != nullptr;
     if (m->trace) {
       for (int i = 0; i < 2; i++)
@@ -813,9 +811,18 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
       TS_CUDA(cudaEventCreate(&m->tr_base));
       TS_CUDA(cudaEventRecord(m->tr_base, 0));
     }
+    // frames per queue launch, alternating a, b, a, b, ...: half a batch each by default, so that the kernels of the
+    // first half run while the caller is still handing over the second half.  (16,48 and 24,40 were measured too: with
+    // page-locked frames the step is bound by the PCIe reads of the row gather, the split hardly matters.)
+    m->queue_launch[0] = TSLAM_MAX_BATCH / 2;
+    m->queue_launch[1] = TSLAM_MAX_BATCH / 2;
     const char* ql = getenv("TSLAM_QUEUE_LAUNCH");
-    m->queue_launch = ql ? atoi(ql) : TSLAM_MAX_BATCH / 2;
-    if (m->queue_launch < 1 || m->queue_launch > TSLAM_MAX_BATCH) m->queue_launch = TSLAM_MAX_BATCH;
+    if (ql) {
+      int a = 0, b = 0;
+      const int k = sscanf(ql, "%d,%d", &a, &b);
+      if (k == 1) b = a;
+      if (k >= 1 && a >= 1 && a <= TSLAM_MAX_BATCH && b >= 1 && b <= TSLAM_MAX_BATCH) { m->queue_launch[0] = a; m->queue_launch[1] = b; }
+    }
   }
   for (int i = 0; i < 2; i++) {
     TS_CUDA(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
@@ -1166,6 +1173,7 @@ static int ts_gather_pending(tslam_tsdf* m) {
 }
 
 static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
+  m->q_phase = 0;  // any launch that is not the queue's own threshold (flush, reader, geometry change) restarts the pattern
   const int n = m->q_n;
   if (n == 0) return TSLAM_OK;
   const int b = m->q_buf;
@@ -1193,6 +1201,7 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
 
 extern "C" int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream) {
   if (!m) return TSLAM_E_INVALID;
+  m->q_phase = 0;
   return ts_launch_queue(m, (cudaStream_t)stream);
 }
 
@@ -1255,7 +1264,12 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;
   m->q_n = q + 1;
-  if (m->q_n == m->queue_launch) return ts_launch_queue(m, st);
+  if (m->q_n >= m->queue_launch[m->q_phase]) {
+    const int ph = m->q_phase;
+    int rc = ts_launch_queue(m, st);
+    m->q_phase = ph ^ 1;
+    return rc;
+  }
   if (m->q_n - m->q_gathered >= TS_GATHER_GROUP) return ts_gather_pending(m);
   return TSLAM_OK;
 }

@@ -65,7 +65,7 @@ class DenseTSDF(BaseMap):
         self._queue_tex = self._h.L.tslam_tsdf_queue_depth_tex
         # page-locked frames are read by the GPU straight from host memory a few calls later (include/tslam.h): keep
         # the arrays alive for as long as the library may still read them (it never runs more than 2 batches ahead)
-        self._frame_refs = collections.deque(maxlen=3 * capi.MAX_BATCH)
+        self._frame_refs = collections.deque(maxlen=6 * capi.MAX_BATCH)  # depth + colour image per frame
         self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._dev_index = torch.cuda.current_device()
         if texture_enabled:
@@ -111,12 +111,15 @@ class DenseTSDF(BaseMap):
         h, w = depthmap.shape
         sid = 0 if self.is_global_map else self.active_submap_id.v
         self._frame_refs.append(depthmap)
-        if self.enable_texture:  # ti.static(self.enable_texture) (:205): the colour image rides along (uint8 [th,tw,3])
+        if self.enable_texture and texture is not None and getattr(texture, "size", 0) > 0:
+            # ti.static(self.enable_texture) (:205): the colour image rides along (uint8 [th,tw,3]); a caller that has no
+            # image for this frame (empty array) integrates geometry only
             if not self.color_same_proj and self.K_cam_color is None:
                 raise RuntimeError("set_color_camera_intrinsic() must be called before recast_depth_to_map (color_same_proj=False)")
             if texture.dtype != np.uint8 or not texture.flags.c_contiguous:
                 texture = np.ascontiguousarray(texture, dtype=np.uint8)
             th, tw = texture.shape[0], texture.shape[1]
+            self._frame_refs.append(texture)
             if self.color_same_proj and (th < h or tw < w):
                 raise ValueError("color_same_proj=True needs a colour image at least as large as the depth image")
             rc = self._queue_tex(self._h.h, depthmap.__array_interface__["data"][0], texture.__array_interface__["data"][0], h, w,
@@ -142,7 +145,7 @@ class DenseTSDF(BaseMap):
         xyz = np.ascontiguousarray(np.asarray(xyz_array, dtype=np.float32).reshape(-1, 3))
         s = 0 if self.is_global_map else self.active_submap_id[None]
         rgb = None
-        if self.enable_texture:  # :179-183
+        if self.enable_texture and rgb_array is not None and np.size(rgb_array) > 0:  # :179-183
             rgb = np.ascontiguousarray(np.asarray(rgb_array, dtype=np.uint8).reshape(-1, 3))
         self._h.integrate_points(xyz, self.input_R_np, self.input_T_np, submap=s, commit=True, rgb=rgb)
         self._torch.cuda.current_stream().synchronize()  # pageable source

@@ -81,7 +81,7 @@ class Octomap(BaseMap):
         self.set_pose(R, T)
         xyz = np.ascontiguousarray(np.asarray(xyz_array, dtype=np.float32).reshape(-1, 3))
         rgb = None
-        if self.enable_texture:  # :142-143 process_point(pt, rgb_array[index]); BGR -> RGB inside (:120-124)
+        if self.enable_texture and rgb_array is not None and np.size(rgb_array) > 0:  # :142-143; BGR -> RGB inside (:120-124)
             rgb = np.ascontiguousarray(np.asarray(rgb_array, dtype=np.uint8).reshape(-1, 3))
         if n is not None:
             xyz = xyz[:n]
@@ -90,7 +90,9 @@ class Octomap(BaseMap):
 
     def recast_depth_to_map(self, R, T, depthmap, texture):
         self.set_pose(R, T)
-        tex = np.ascontiguousarray(texture, dtype=np.uint8) if self.enable_texture else None  # :160-167
+        tex = None
+        if self.enable_texture and texture is not None and np.size(texture) > 0:  # :160-167
+            tex = np.ascontiguousarray(texture, dtype=np.uint8)
         self._h.integrate_depth(np.asarray(depthmap), self.input_R_np, self.input_T_np, submap=self._active(), texture=tex)
 
     # :90-114

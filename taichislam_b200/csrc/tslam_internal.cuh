@@ -295,6 +295,12 @@ struct tslam_octo {
   int sm_count;
 };
 
+// 64-bit max without a return value: RED.E.MAX.64 (atomicMax(unsigned long long*) with an unused result was lowered
+// to ATOMG - a response sector per update, seen as 57 M "L2 ATOM sectors" per textured launch in ncu)
+__device__ __forceinline__ void ts_red_max_u64(unsigned long long* addr, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
 // colour pixel of depth pixel (i, j): texture[j, i] (color_same_proj) or color_ind_from_depth_pt
 // (mapping_common.py:43-58).  The reference tests color_i against h and color_j against w (swapped, :56); what passes
 // that test but lies outside the image is an out-of-bounds read there - pixel (0,0) here.  Returns false when even the

@@ -14,7 +14,7 @@ __device__ __forceinline__ void oc_hit(const OcGrid& g, int s, int i, int j, int
   if (blk < 0) return;
   const size_t o = (size_t)blk * OC_B3 + oc_voxel_off(i, j, k);
   atomicAdd(&g.cnt[o], add);  // occupy[ijk] += 1 (:119)
-  if (cw) atomicMax(&g.cw[o], cw);
+  if (cw) ts_red_max_u64(&g.cw[o], cw);
 }
 // "Stupid OpenCV is BGR" (:121): colour channel 0 <- rgb[2], 2 <- rgb[0]
 __device__ __forceinline__ unsigned long long oc_color_word(unsigned int seq, const uint8_t* p) {

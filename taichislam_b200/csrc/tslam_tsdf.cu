@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
         red_add_f32x2(&g.acc[vo], a, wgt);  // :264,:267
         if (TEX) {  // color[xi] = ray colour (:268-269): latest frame, then the sample closest to its surface point
           const int cl = min(4095, (int)(fabsf(ds) / vs * 16.0f));
-          atomicMax(&g.cword[vo], cw_hi | ((unsigned long long)(4095 - cl) << 30));
+          ts_red_max_u64(&g.cword[vo], cw_hi | ((unsigned long long)(4095 - cl) << 30));
         }
         my_updates++;
       }
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       const float B = (float)(((double)bhi * 4294967296.0 + (double)blo) * (1.0 / 16777216.0));
       red_add_f32x2(&g.acc[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], A, B);
       if (TEX) {
-        atomicMax(&g.cword[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], w_cw[e]);
+        ts_red_max_u64(&g.cword[(size_t)blk * TS_B3 + ts_voxel_off(xi, yi, zi)], w_cw[e]);
         w_cw[e] = 0ull;
       }
     }

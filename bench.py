@@ -46,8 +46,9 @@ def load_traffic(kernel):
             if fn.endswith("_traffic.json"):
                 try:
                     d = json.load(open(os.path.join(pdir, fn)))
-                    if kernel in d:
-                        best = (float(d[kernel]), fn)
+                    for key, val in d.items():  # exact name, or the template instance ("void k_raymarch<0>")
+                        if key == kernel or (kernel + "<0>") in key:
+                            best = (float(val), fn)
                 except Exception:
                     pass
     return best

@@ -209,7 +209,9 @@ def run_reference(args, rank, world):
     from taichislam_b200 import synthetic as syn
     cores = os.cpu_count() or 1
     maps = [OracleTSDF(map_scale=MAP_SCALE, K=syn.K_DEPTH, is_global_map=True) for _ in range(cores)]
-    per_step = 2 * cores  # bounded sample per step
+    # bounded sample per step: one or two frames per host thread, so that K steps stay within a few minutes
+    # (~0.3 s per 128-frame step on 128 cores)
+    per_step = cores if args.steps > 50 else 2 * cores
     t = 0
     for _ in range(args.warmup):
         d, Rs, Ts = make_inputs(per_step, t)

@@ -11,5 +11,6 @@ from .dense_tsdf import DenseTSDF, Wmax  # noqa: F401
 from .taichi_octomap import Octomap  # noqa: F401
 from .marching_cube_mesher import MarchingCubeMesher  # noqa: F401
 from .submap_mapping import SubmapMapping  # noqa: F401
+from .topo_graph import TopoGraphGen  # noqa: F401
 
-__all__ = ["DenseTSDF", "Octomap", "MarchingCubeMesher", "BaseMap", "SubmapMapping", "ti", "np", "math", "time", "sign", "Wmax"]
+__all__ = ["DenseTSDF", "Octomap", "MarchingCubeMesher", "BaseMap", "SubmapMapping", "TopoGraphGen", "ti", "np", "math", "time", "sign", "Wmax"]

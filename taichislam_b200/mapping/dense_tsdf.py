@@ -276,6 +276,19 @@ class DenseTSDF(BaseMap):
         self.set_base_pose_submap(idx, R, T)
         return idx
 
+    # ------------------------------------------------------------------ planner queries (mapping_common.py:165-204)
+    def _query_raycast(self, pos, dir, max_dist):
+        self._flush()
+        return self._h.raycast(pos, dir, max_dist, submap=self._active())
+
+    def _query_points(self, xyz):
+        self._flush()
+        return self._h.query_points(xyz, submap=self._active())   # (is_occupy, is_unobserved), dense_tsdf.py:148-155
+
+    def _query_near(self, xyz, voxel):
+        self._flush()
+        return self._h.query_near_occupy(xyz, voxel, submap=self._active())
+
     # ------------------------------------------------------------------ extras (not in the reference)
     def frame_counters(self):
         """Flush, commit and read the integrate counters back (bench.py end-to-end arm)."""

@@ -103,3 +103,43 @@ class BaseMap:
         np.matmul(Rbi, self._pose_tmp_d, out=self._pose_tmp_T)
         self.input_R_np[...] = self._pose_tmp_R
         self.input_T_np[...] = self._pose_tmp_T
+
+    # ------------------------------------------------------------------ planner queries (:165-204)
+    # The reference exposes these as @ti.func helpers that other Taichi kernels (TopoGraphGen) call per ray / per
+    # point.  Here they are host-callable and BATCHED: xyz / pos / dir are [n,3] (or a single [3]) arrays in the frame
+    # of the active submap, every call is one kernel over the whole batch.  Subclasses implement the _query_* hooks.
+    @staticmethod
+    def _as_batch(a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        return (a.reshape(1, 3), True) if a.ndim == 1 else (a.reshape(-1, 3), False)
+
+    def raycast(self, pos, dir, max_dist):
+        """(succ, last position, length) of BaseMap.raycast (:165-178) for every ray."""
+        p, single = self._as_batch(pos)
+        d, _ = self._as_batch(dir)
+        succ, x, ln = self._query_raycast(p, d, float(max_dist))
+        return (bool(succ[0]), x[0], float(ln[0])) if single else (succ, x, ln)
+
+    def is_pos_occupy(self, xyz):  # :188-192
+        p, single = self._as_batch(xyz)
+        r = self._query_points(p)[0]
+        return bool(r[0]) if single else r
+
+    def is_pos_unobserved(self, xyz):  # :181-185
+        p, single = self._as_batch(xyz)
+        r = self._query_points(p)[1]
+        return bool(r[0]) if single else r
+
+    def is_near_pos_occupy(self, xyz, voxel):  # :194-204 (range(-voxel, voxel): voxel = 0 tests nothing)
+        p, single = self._as_batch(xyz)
+        r = self._query_near(p, int(voxel))
+        return bool(r[0]) if single else r
+
+    def _query_raycast(self, pos, dir, max_dist):
+        raise NotImplementedError("Not implemented")  # mapping_common.py:207-214
+
+    def _query_points(self, xyz):
+        raise NotImplementedError("Not implemented")
+
+    def _query_near(self, xyz, voxel):
+        raise NotImplementedError("Not implemented")

@@ -115,6 +115,14 @@ class Octomap(BaseMap):
         print(f"[OctoMap] Fuse submaps {(time.time() - t) * 1000:.1f}ms, active local: {submaps.active_submap_id[None]} "
               f"remote: {submaps.remote_submap_num[None]}")
 
+    # planner queries (mapping_common.py:165-204; is_occupy :86-88; the reference's Octomap has no is_unobserved)
+    def _query_raycast(self, pos, dir, max_dist):
+        return self._h.raycast(pos, dir, max_dist, submap=self._active())
+
+    def _query_points(self, xyz):
+        occ = self._h.query_points(xyz, submap=self._active())
+        return occ, np.zeros(len(occ), bool)  # BaseMap.is_unobserved prints "Not implemented" and returns False (:207-209)
+
     def saveMap(self, path):  # :201-202 (stub in the reference)
         pass
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def test_star_import_namespace():
     ns = {}
     exec("from taichi_slam.mapping import *", ns)
-    for name in ("DenseTSDF", "Octomap", "SubmapMapping", "BaseMap", "MarchingCubeMesher", "ti", "np", "math", "time"):
+    for name in ("DenseTSDF", "Octomap", "SubmapMapping", "BaseMap", "MarchingCubeMesher", "TopoGraphGen", "ti", "np", "math", "time"):
         assert name in ns
     ns["ti"].init(arch=ns["ti"].cuda, dynamic_index=True, debug=False, device_memory_GB=4)  # taichislam_node.py:34
     with pytest.raises(RuntimeError):

@@ -123,6 +123,11 @@ class Octomap(BaseMap):
         occ = self._h.query_points(xyz, submap=self._active())
         return occ, np.zeros(len(occ), bool)  # BaseMap.is_unobserved prints "Not implemented" and returns False (:207-209)
 
+    def _query_near(self, xyz, voxel):
+        if int(voxel) <= 0:  # range(-voxel, voxel) is empty (mapping_common.py:198): what TopoGraphGen asks for (:328)
+            return np.zeros(len(xyz), bool)
+        raise NotImplementedError("Octomap.is_near_pos_occupy(voxel > 0) has no batched kernel yet")
+
     def saveMap(self, path):  # :201-202 (stub in the reference)
         pass
 

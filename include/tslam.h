@@ -92,8 +92,9 @@ int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, 
                                const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream);
 /* Per-frame form of the same call, for callers that hand over one frame at a time (the reference API):
  * copies ONE host frame to a device staging slot on an internal copy stream (overlapping the kernels of the
- * previous batch) and records its pose; TSLAM_MAX_BATCH queued frames - or tslam_tsdf_flush, which every
- * reader calls implicitly - are integrated and committed with one launch triple.  Pageable frames may be reused
+ * previous launch) and records its pose; every TSLAM_MAX_BATCH/2 queued frames (TSLAM_QUEUE_LAUNCH="a,b" in the
+ * environment alternates other counts) - or tslam_tsdf_flush, which every reader calls implicitly - are integrated
+ * and committed with one launch triple, so the kernels of one half run while the caller hands over the next.  Pageable frames may be reused
  * immediately.  PAGE-LOCKED (pinned / cudaHostRegister'ed) frames are not copied at all: the GPU fetches their
  * sampled rows (every recast_step-th row) straight from host memory a few calls later - half the PCIe bytes for
  * recast_step 2 - so they must stay valid and unchanged until tslam_tsdf_flush has returned and the stream has

@@ -3,9 +3,11 @@
 Same constructor kwargs, attributes and methods as the reference class (SURVEY.md section 8b);
 every method that launched a Taichi kernel now enqueues hand-written sm_100a kernels through
 the C ABI (include/tslam.h).  Like Taichi, calls are asynchronous: `recast_depth_to_map`
-queues the frame (pinned staging + pose) and frames are integrated in batches of up to 64 per
-launch; any reader (`count_active`, `to_numpy`, `cvt_*`, field reads, the mesher) flushes the
-queue first, so results are indistinguishable from per-frame execution.
+hands the frame and its pose to the library's queue (pageable arrays are copied at once, page-locked
+ones are fetched by the GPU itself a few calls later) and the queue integrates every 32 frames with
+one launch triple; any reader (`count_active`, `to_numpy`, `cvt_*`, field reads, the mesher, the
+planner queries) flushes the queue first, so results are indistinguishable from per-frame execution
+(up to the commit-granularity note in DESIGN.md for voxels saturated at Wmax).
 """
 import collections
 import math

@@ -65,3 +65,70 @@ def test_topo_sample_directions_are_the_fibonacci_sphere():
     assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-6)
     assert np.allclose(d[0], [0, 1, 0], atol=1e-7) and np.allclose(d[-1], [0, -1, 0], atol=1e-6)
     assert abs(d.mean(0)).max() < 0.02  # evenly spread
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Replay of golden vectors produced by the REFERENCE'S OWN host-side code (tools/make_golden_host.py: the unmodified
+# classes of /root/reference executed with a stand-in taichi module): constructor arithmetic, convert_by_base, the
+# TopoGraphGen ray directions.  These rows of the path are therefore pinned against the reference itself.
+# ---------------------------------------------------------------------------------------------------------------
+import json
+import os
+from unittest import mock
+
+HOST_GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_reference.json")))
+
+
+def _unhex(v):
+    return float.fromhex(v) if isinstance(v, str) else v
+
+
+def _construct_without_gpu(cls_name, kwargs):
+    """Run the class constructor's host arithmetic with the device handle stubbed out (no GPU in the CPU suite)."""
+    import taichislam_b200.mapping.dense_tsdf as dt
+    import taichislam_b200.mapping.taichi_octomap as oc
+    import torch
+    with mock.patch.object(dt, "TsdfHandle", mock.MagicMock()), mock.patch.object(oc, "OctoHandle", mock.MagicMock()), \
+            mock.patch.object(dt.DenseTSDF, "_init_export_fields", lambda self: None), \
+            mock.patch.object(torch.cuda, "current_device", lambda: 0), \
+            mock.patch.object(oc, "Field", mock.MagicMock()), mock.patch.object(torch, "zeros", mock.MagicMock()), \
+            mock.patch.object(torch, "full", mock.MagicMock()), mock.patch.object(torch, "device", mock.MagicMock()):
+        return (dt.DenseTSDF if cls_name == "DenseTSDF" else oc.Octomap)(**kwargs)
+
+
+def test_constructor_arithmetic_matches_reference():
+    for case in HOST_GOLD["dense_tsdf_ctor"]:
+        m = _construct_without_gpu("DenseTSDF", case["kwargs"])
+        for k, v in case["attrs"].items():
+            assert getattr(m, k) == _unhex(v), (case["kwargs"], k, getattr(m, k), _unhex(v))
+    for case in HOST_GOLD["octomap_ctor"]:
+        m = _construct_without_gpu("Octomap", case["kwargs"])
+        for k, v in case["attrs"].items():
+            assert getattr(m, k) == _unhex(v), (case["kwargs"], k, getattr(m, k), _unhex(v))
+
+
+def test_convert_by_base_matches_reference_bitwise():
+    for c in HOST_GOLD["convert_by_base"]:
+        m = _Map(0.05)
+        arr = lambda key, shape: np.array([float.fromhex(x) for x in c[key]]).reshape(shape)  # noqa: E731
+        m.base_R_np, m.base_T_np = arr("base_R", (3, 3)), arr("base_T", 3)
+        if c["submap_enabled"]:
+            m.initialize_submap_fields(4)
+            m.submaps_base_R_np[:] = arr("sub_R", (4, 3, 3))
+            m.submaps_base_T_np[:] = arr("sub_T", (4, 3))
+            m.active_submap_id[None] = c["sid"]
+        R, T = arr("R", (3, 3)), arr("T", 3)
+        R_, T_ = m.convert_by_base(R, T)
+        assert np.array_equal(R_, arr("R_out", (3, 3))) and np.array_equal(T_, arr("T_out", 3))
+        m.set_pose(R, T)
+        assert np.array_equal(m.input_R_np, arr("R_out", (3, 3)).astype(np.float32))
+        assert np.array_equal(m.input_T_np, arr("T_out", 3).astype(np.float32))
+
+
+def test_topo_sample_dirs_match_reference_bitwise():
+    from taichislam_b200.mapping.topo_graph import TopoGraphGen
+    for n, vals in HOST_GOLD["topo_sample_dirs_f32"].items():
+        t = TopoGraphGen.__new__(TopoGraphGen)
+        t.generate_uniform_sample_points(int(n))
+        ref = np.array([float.fromhex(v) for v in vals], np.float32).reshape(int(n), 3)
+        assert np.array_equal(t.sample_dirs, ref)

@@ -132,3 +132,35 @@ def test_topo_sample_dirs_match_reference_bitwise():
         t.generate_uniform_sample_points(int(n))
         ref = np.array([float.fromhex(v) for v in vals], np.float32).reshape(int(n), 3)
         assert np.array_equal(t.sample_dirs, ref)
+
+
+def test_submap_mapping_call_trace_matches_reference():
+    """The scripted session of tests/submap_scenario.py through taichislam_b200.mapping.SubmapMapping, map methods
+    replaced by recorders: the trace (which map receives which call with which bit-exact pose, what goes on the wire,
+    final submap table) equals the one recorded from the REFERENCE's SubmapMapping.  Only difference allowed: the
+    reference's hard-coded `saveMap("/home/xuhao/output/test_map.npy")` (submap_mapping.py:144-145) is opt-in here."""
+    import contextlib
+    import io
+    import submap_scenario as sc
+    import taichislam_b200.mapping.dense_tsdf as dt
+    import taichislam_b200.mapping.submap_mapping as smm
+    rec = sc.Recorder()
+
+    def light_init(self, map_scale=[10, 10], voxel_scale=0.05, texture_enabled=False, max_disp_particles=1024 * 1024,
+                   is_global_map=False, **kw):
+        self.is_global_map = is_global_map
+        self.enable_texture = texture_enabled
+        self.max_disp_particles = max_disp_particles
+        self.export_color = self.export_TSDF_xyz = self.num_TSDF_particles = object()
+
+    with contextlib.ExitStack() as st:
+        st.enter_context(mock.patch.object(dt.DenseTSDF, "__init__", light_init))
+        for pch in rec.patches(dt.DenseTSDF):
+            st.enter_context(pch)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sc.run(smm.SubmapMapping, dt.DenseTSDF, rec)
+    ref = [e for e in HOST_GOLD["submap_mapping_trace"] if e[1] != "saveMap"]
+    got = json.loads(json.dumps([e for e in rec.trace if e[1] != "saveMap"]))
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a == b, (a[:3], b[:3])

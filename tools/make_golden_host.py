@@ -123,6 +123,20 @@ def main():
         arr = np.stack([np.asarray(o.sample_dirs[i], dtype=np.float32) for i in range(n)])
         dirs[str(n)] = [float(v).hex() for v in arr.reshape(-1)]
     g["topo_sample_dirs_f32"] = dirs
+
+    # 5. SubmapMapping orchestration (submap_mapping.py): the call trace of a scripted session (tests/submap_scenario.py)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import contextlib
+    import io as _io
+    import submap_scenario as sc
+    from taichi_slam.mapping.submap_mapping import SubmapMapping
+    rec = sc.Recorder()
+    with contextlib.ExitStack() as st:
+        for pch in rec.patches(DenseTSDF):
+            st.enter_context(pch)
+        with contextlib.redirect_stdout(_io.StringIO()):
+            sc.run(SubmapMapping, DenseTSDF, rec)
+    g["submap_mapping_trace"] = rec.trace
     json.dump(g, open(OUT, "w"), indent=0)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

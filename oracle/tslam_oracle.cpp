@@ -9,14 +9,25 @@
 // `--impl reference` legs may load this library.  The product
 // (taichislam_b200/) never links, imports or calls it.
 //
-// PARITY STATUS: *unpinned at the Taichi boundary*.  Taichi cannot be imported
-// or installed in the build container, the reference ships no golden vectors
-// for integrate / octomap / marching cubes / ESDF and its kernels are racy
-// (non-atomic RMW from concurrent rays, f16 atomics in arbitrary order).  The
-// oracle is therefore a *deterministic canonicalisation* of the source text.
-// What IS pinned by reference artefacts: the two exported maps in data/*.npy
-// (schema, counts, load->export round trip; tests/test_golden_fixtures.py) and
-// the marching-cubes case tables (sha256, tests/test_mc_tables.py).
+// PARITY STATUS: *unpinned at the Taichi boundary* - Taichi itself cannot be
+// imported or installed in the build container, the reference ships no golden
+// vectors for integrate / octomap / marching cubes / ESDF and its kernels are
+// racy (non-atomic RMW from concurrent rays, f16 atomics in arbitrary order), so
+// the oracle is a *deterministic canonicalisation* of the source text.
+// What IS pinned:
+//   * by the reference's KERNEL SOURCE, EXECUTED: oracle/taichi_emu.py runs the
+//     unmodified kernels of /root/reference in Python with Taichi's f16/f32 value
+//     typing (one legal serial schedule); tools/make_golden_ref.py stores what they
+//     compute (tests/golden/ref_exec.npz) and tests/test_oracle_vs_reference_exec.py
+//     replays the inputs here: MODE_F16_FAITHFUL reproduces depth / point-cloud
+//     integration with identical voxel sets and > 99.8 % bit-equal TSDF / W, the
+//     exporters, load/save, marching cubes (same triangles), submap fusion (same
+//     voxels, same NaN pattern) and the Octomap counts exactly.  ESDF (dead code in
+//     the reference) stays unpinned.  Residual: the emulation is not Taichi's LLVM
+//     backend (no FMA contraction, no races).
+//   * by reference artefacts: the two exported maps in data/*.npy (schema, counts,
+//     load->export round trip), the marching-cubes case tables (sha256), and the
+//     host-side code of the classes run directly (tests/golden/host_reference.json).
 //
 // Numeric modes (TSDF integrate):
 //   MODE_CANONICAL (0)  the mode the CUDA path is compared against bit-for-bit

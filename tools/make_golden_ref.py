@@ -1,0 +1,168 @@
+#!/usr/bin/env python3
+"""Golden vectors from the REFERENCE'S OWN KERNELS, executed - build container only (/root/reference must exist).
+
+oracle/taichi_emu.py is a stand-in for the `taichi` package that runs the reference's unmodified kernel source in
+Python with Taichi's value typing (f16 fields, f32 default) on one legal serial schedule.  This script drives the
+reference classes exactly as their callers do (set_dep_camera_intrinsic / set_base_pose_submap / recast_* / fuse /
+export / generate_mesh) on small seeded inputs and stores the resulting map state in
+tests/golden/ref_exec.npz; tests/test_oracle_vs_reference_exec.py replays the same inputs through the oracle.
+
+Run from anywhere:  python tools/make_golden_ref.py        (takes a few minutes: the kernels run as Python loops)
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path = [p for p in sys.path if os.path.abspath(p or ".") != ROOT] + [ROOT, os.path.join(ROOT, "tests")]
+from oracle import taichi_emu as emu  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "ref_exec.npz")
+
+
+def state(m, submap=None):
+    """observed voxels of a reference DenseTSDF: idx int16[n,3] (+ submap), TSDF f16, W f16; occupy cells separately."""
+    keys = sorted(k for k, v in m.TSDF_observed.d.items() if v > 0 and (submap is None or k[0] == submap))
+    idx = np.array([k[1:] for k in keys], np.int16).reshape(-1, 3)
+    t = np.array([m.TSDF.d[k] for k in keys], np.float16)
+    w = np.array([m.W_TSDF.d[k] for k in keys], np.float16)
+    occ = np.array([m.occupy.d.get(k, 0) for k in keys], np.int8)
+    occ_cells = np.array(sorted(k[1:] for k, v in m.occupy.d.items() if v != 0 and (submap is None or k[0] == submap)), np.int16).reshape(-1, 3)
+    return idx, t, w, occ, occ_cells
+
+
+def inputs():
+    from taichislam_b200 import synthetic as syn
+    from util import rot_xyz
+    K = [v / 4 if i in (0, 2, 4, 5) else v for i, v in enumerate(syn.K_DEPTH)]
+    d1 = np.minimum(syn.scene_room()[::4, ::4], 2800).astype(np.uint16)
+    d2 = np.minimum(syn.scene_sphere(2.5)[::4, ::4], 2800).astype(np.uint16)
+    P1 = (rot_xyz(0.1, -0.05, 0.3), np.array([0.2, -0.1, 0.05]))
+    P2 = (rot_xyz(-0.05, 0.1, 0.25), np.array([0.25, -0.05, 0.1]))
+    rng = np.random.default_rng(11)
+    dirs = rng.normal(size=(2500, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    pcl = (dirs * rng.uniform(0.5, 3.4, (2500, 1))).astype(np.float32)   # some beyond max_ray_length: filtered (:177)
+    return K, d1, d2, P1, P2, pcl
+
+
+def main():
+    t00 = time.time()
+    ref = emu.load_reference()
+    D, O, MC = ref.dense_tsdf.DenseTSDF, ref.taichi_octomap.Octomap, ref.marching_cube_mesher.MarchingCubeMesher
+    K, d1, d2, P1, P2, pcl = inputs()
+    g = {"K": np.array(K), "d1": d1, "d2": d2, "P1_R": P1[0], "P1_T": P1[1], "P2_R": P2[0], "P2_T": P2[1], "pcl": pcl}
+    kw = dict(map_scale=[6.4, 6.4], voxel_scale=0.05, num_voxel_per_blk_axis=16, max_ray_length=3.0, max_disp_particles=1 << 17,
+              max_submap_num=4)
+    e = np.array([])
+
+    # A. global map: frame 1, then frame 2 on top (dense_tsdf.py:162-165, :188-270)
+    m = D(is_global_map=True, **kw)
+    m.set_dep_camera_intrinsic(K)
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    m.recast_depth_to_map(P1[0], P1[1], d1, e)
+    for n, a in zip(("idx", "T", "W", "occ", "occcells"), state(m)):
+        g["A1_" + n] = a
+    print(f"A1 {len(g['A1_idx'])} voxels, {time.time() - t00:.0f}s")
+    # F. exporters / IO on that state (:339-365, :412-454)
+    g["F_count_active"] = np.array(int(m.count_active()))
+    n = int(g["F_count_active"])
+    di, dt_, dw, do, dc = np.zeros((n, 3), np.int16), np.zeros(n, np.float16), np.zeros(n, np.float16), np.zeros(n, np.int8), np.array([])
+    m.to_numpy(di, dt_, dw, do, dc)
+    g["F_to_numpy_idx"], g["F_to_numpy_T"], g["F_to_numpy_W"], g["F_to_numpy_occ"] = di, dt_, dw, do
+    m.disp_floor, m.disp_ceiling = -3.0, 3.0
+    m2 = D(is_global_map=True, disp_floor=-3.0, disp_ceiling=3.0, **kw)   # same map with a display range that keeps everything
+    m2.load_numpy(0, di, dt_, dw, do, dc)
+    m2.cvt_TSDF_surface_to_voxels()
+    ns = int(m2.num_TSDF_particles[None])
+    g["F_surface_xyz"] = m2.export_TSDF_xyz.to_numpy()[:ns].astype(np.float32)
+    g["F_loaded_count"] = np.array(int(m2.count_active()))
+    # H. marching cubes on the loaded map (marching_cube_mesher.py:127-187), step 1
+    mesher = MC(m2, max_triangles=200000, tsdf_surface_thres=0.1)
+    mesher.generate_mesh(1)
+    nt = int(mesher.num_facelets[None])
+    g["H_mc_triangles"] = np.array(nt)
+    g["H_mc_vertices"] = mesher.mesh_vertices.to_numpy()[:3 * nt].astype(np.float32)
+    g["H_mc_normals"] = mesher.mesh_normals.to_numpy()[:3 * nt].astype(np.float32)
+    print(f"F/H surface {ns}, triangles {nt}, {time.time() - t00:.0f}s")
+    m.recast_depth_to_map(P2[0], P2[1], d2, e)
+    for n, a in zip(("idx", "T", "W", "occ", "occcells"), state(m)):
+        g["A2_" + n] = a
+    print(f"A2 {len(g['A2_idx'])} voxels, {time.time() - t00:.0f}s")
+
+    # C. point-cloud variant (:167-186)
+    m = D(is_global_map=True, **kw)
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    m.recast_pcl_to_map(P1[0], P1[1], pcl, e)
+    for n, a in zip(("idx", "T", "W", "occ", "occcells"), state(m)):
+        g["C_" + n] = a
+    print(f"C {len(g['C_idx'])} voxels, {time.time() - t00:.0f}s")
+
+    # E. submap collection + fusion into a global map (:272-318)
+    from util import rot_xyz
+    sub = D(is_global_map=False, **kw)
+    sub.set_dep_camera_intrinsic(K)
+    glo = D(is_global_map=True, **dict(kw, map_scale=[12.8, 12.8]))
+    base = [(rot_xyz(0.1, 0.2, 0.3), np.array([0.5, 0.1, -0.2])), (rot_xyz(-0.3, 0.1, 1.0), np.array([-0.4, 0.6, 0.3]))]
+    dsmall = d1[::2, ::2].copy()
+    Ks = [v / 2 if i in (0, 2, 4, 5) else v for i, v in enumerate(K)]
+    sub.set_dep_camera_intrinsic(Ks)
+    for s, (Rb, Tb) in enumerate(base):
+        sub.set_base_pose_submap(s, Rb, Tb)
+        glo.set_base_pose_submap(s, Rb, Tb)
+        Rw, Tw = Rb @ P1[0], Rb @ P1[1] + Tb          # world pose whose submap-relative pose is P1
+        sub.recast_depth_to_map(Rw, Tw, dsmall, e)
+        for n, a in zip(("idx", "T", "W", "occ", "occcells"), state(sub, s)):
+            g[f"E_sub{s}_" + n] = a
+        if s == 0:
+            sub.switch_to_next_submap()
+    glo.fuse_submaps(sub)
+    keys = sorted(k for k, v in glo.TSDF_observed.d.items() if v > 0)
+    g["E_glo_idx"] = np.array([k[1:] for k in keys], np.int16)
+    g["E_glo_T"] = np.array([glo.TSDF.d[k] for k in keys], np.float16)
+    g["E_glo_W"] = np.array([glo.W_TSDF.d[k] for k in keys], np.float16)
+    g["E_glo_occ"] = np.array([glo.occupy.d.get(k, 0) for k in keys], np.int8)
+    g["E_base_R"], g["E_base_T"], g["E_dsmall"], g["E_K"] = np.stack([b[0] for b in base]), np.stack([b[1] for b in base]), dsmall, np.array(Ks)
+    print(f"E fused {len(keys)} voxels, {time.time() - t00:.0f}s")
+
+    # G. Octomap: points, depth, fusion, level-1 export (taichi_octomap.py:116-199)
+    okw = dict(map_scale=[6.4, 6.4], voxel_scale=0.05, min_occupy_thres=1, K=2, max_ray_length=3.0, max_submap_num=4, max_disp_particles=1 << 17)
+    oc = O(**okw)
+    oc.set_dep_camera_intrinsic(K)
+    oc.set_base_pose_submap(0, base[0][0], base[0][1])
+    Rw, Tw = base[0][0] @ P1[0], base[0][0] @ P1[1] + base[0][1]
+    oc.recast_pcl_to_map(Rw, Tw, pcl, e, len(pcl))
+    oc.recast_depth_to_map(Rw, Tw, d1, e)
+    keys = sorted(k for k, v in oc.occupy.d.items() if v > 0)
+    g["G_idx"] = np.array([k[1:] for k in keys], np.int16)
+    g["G_count"] = np.array([oc.occupy.d[k] for k in keys], np.float32)
+    oc.cvt_occupy_to_voxels(1)
+    ne = int(oc.num_export_particles[None])
+    g["G_export_xyz"] = oc.export_x.to_numpy()[:ne].astype(np.float32)
+    # fusion: the reference's Octomap.fuse_submaps reads `submaps.color`, which only exists with texture_enabled=True
+    # (taichi_octomap.py:77-79, :198) - an untextured Octomap cannot be fused there (AttributeError).  Textured pair:
+    from taichislam_b200 import synthetic as syn
+    tex = syn.texture_gradient(9, d1.shape[0], d1.shape[1])
+    rgb = np.random.default_rng(3).integers(0, 256, (len(pcl), 3)).astype(np.uint8)
+    oct_ = O(**dict(okw, texture_enabled=True))
+    oct_.set_dep_camera_intrinsic(K)
+    oct_.set_base_pose_submap(0, base[0][0], base[0][1])
+    oct_.recast_pcl_to_map(Rw, Tw, pcl, rgb, len(pcl))
+    oct_.recast_depth_to_map(Rw, Tw, d1, tex)
+    og = O(**dict(okw, map_scale=[12.8, 12.8], is_global_map=True, texture_enabled=True))
+    og.set_base_pose_submap(0, base[0][0], base[0][1])
+    og.fuse_submaps(oct_)
+    keys = sorted(k for k, v in og.occupy.d.items() if v > 0)
+    g["G_fused_idx"] = np.array([k[1:] for k in keys], np.int16)
+    g["G_fused_count"] = np.array([og.occupy.d[k] for k in keys], np.float32)
+    g["G_tex"], g["G_rgb"] = tex, rgb
+    print(f"G octomap {len(g['G_idx'])} voxels, fused {len(keys)}, {time.time() - t00:.0f}s")
+
+    np.savez_compressed(OUT, **g)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

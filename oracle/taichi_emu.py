@@ -417,6 +417,62 @@ def _identity_decorator(*a, **k):
     return a[0] if (len(a) == 1 and callable(a[0]) and not k) else (lambda f: f)
 
 
+class _VecType:
+    """ti.types.vector(n, dtype): a type token usable in @ti.dataclass annotations."""
+
+    def __init__(self, n, dt):
+        self.n, self.dt = n, dt
+
+    def __call__(self, *a):
+        return _vec(list(a[0]) if len(a) == 1 else list(a), self.dt)
+
+
+def _zero_of(tp):
+    if isinstance(tp, _VecType):
+        return _vec(np.zeros(tp.n), tp.dt if tp.dt is not None else f32)
+    npd = _npdt(tp)
+    if npd is not None and np.issubdtype(npd, np.floating):
+        return np.float32(0.0)
+    return 0
+
+
+class _StructField:
+    """<Struct>.field(shape=n): elements are created on first access and handed out by reference."""
+
+    def __init__(self, cls):
+        self.cls, self.items = cls, {}
+
+    def __getitem__(self, i):
+        k = _key(i)
+        it = self.items.get(k)
+        if it is None:
+            it = self.items[k] = self.cls()
+        return it
+
+    def __setitem__(self, i, v):
+        self.items[_key(i)] = v
+
+
+def ti_dataclass(cls):
+    """@ti.dataclass: annotated members become zero-initialised attributes, @ti.func methods stay methods."""
+    ann = dict(getattr(cls, "__annotations__", {}))
+
+    def __init__(self, **kw):
+        for name, tp in ann.items():
+            setattr(self, name, kw.get(name, _zero_of(tp)))
+
+    cls.__init__ = __init__
+    cls.field = classmethod(lambda c, shape=None, **k: _StructField(c))
+    return cls
+
+
+def emu_atomic_add_(container, key, v):
+    """ti.atomic_add(container[key], v) in expression position (rewritten by the loader)."""
+    old = container[key]
+    container[key] = old + v
+    return old
+
+
 def cast(v, dt):
     npd = _npdt(dt)
     if isinstance(v, Vec):
@@ -483,9 +539,50 @@ def ti_static(*a):
     return a[0] if len(a) == 1 else a
 
 
+class I32(int):
+    """A RUNTIME i32 value (loop index).  int (+) Python float happens in f32 in a Taichi kernel (the float is an f32
+    constant there), not in Python's f64: `_len = _j * self.voxel_scale` (mapping_common.py:173) is an f32 product."""
+
+    def _f(self, o, op):
+        if isinstance(o, float) and not isinstance(o, np.floating):
+            return op(np.float32(int(self)), np.float32(o))
+        return NotImplemented
+
+    def __mul__(self, o):
+        r = self._f(o, np.multiply)
+        return r if r is not NotImplemented else (I32(int(self) * int(o)) if isinstance(o, int) and not isinstance(o, bool) else int.__mul__(self, o) if isinstance(o, int) else NotImplemented)
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        r = self._f(o, np.add)
+        return r if r is not NotImplemented else (I32(int(self) + int(o)) if isinstance(o, int) else NotImplemented)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        r = self._f(o, np.subtract)
+        return r if r is not NotImplemented else (I32(int(self) - int(o)) if isinstance(o, int) else NotImplemented)
+
+    def __rsub__(self, o):
+        if isinstance(o, float) and not isinstance(o, np.floating):
+            return np.float32(o) - np.float32(int(self))
+        return I32(int(o) - int(self)) if isinstance(o, int) else NotImplemented
+
+    def __truediv__(self, o):
+        if isinstance(o, (int, float)) and not isinstance(o, np.floating):
+            return np.float32(int(self)) / np.float32(o)
+        return NotImplemented
+
+    def __rtruediv__(self, o):
+        if isinstance(o, (int, float)) and not isinstance(o, np.floating):
+            return np.float32(o) / np.float32(int(self))
+        return NotImplemented
+
+
 def ti_range(*args):
-    """range() with Taichi's implicit float -> int conversion of the bounds (truncation)."""
-    return range(*[int(a) for a in args])
+    """range() with Taichi's implicit float -> int conversion of the bounds (truncation); yields runtime i32 values."""
+    return (I32(v) for v in range(*[int(a) for a in args]))
 
 
 def ti_sign(val):  # mapping_common.py:5-7 `(0 < val) - (val < 0)`
@@ -500,9 +597,9 @@ def make_ti():
     ti = types.ModuleType("taichi")
     ti.__dict__.update(dict(
         f16=f16, f32=f32, f64=f64, i8=i8, i16=i16, i32=i32, i64=i64, u8=u8, u16=u16, u32=u32, int32=int32, float32=float32,
-        kernel=_identity_decorator, func=_identity_decorator, data_oriented=_identity_decorator, dataclass=_identity_decorator,
+        kernel=_identity_decorator, func=_identity_decorator, data_oriented=_identity_decorator, dataclass=ti_dataclass,
         static=ti_static, template=lambda *a, **k: None,
-        types=types.SimpleNamespace(ndarray=lambda *a, **k: None, vector=lambda *a, **k: None, matrix=lambda *a, **k: None),
+        types=types.SimpleNamespace(ndarray=lambda *a, **k: None, vector=lambda n, dt=None: _VecType(n, dt), matrix=lambda *a, **k: None),
         Vector=Vector, Matrix=Matrix, field=lambda dtype=None, shape=None, **k: Field(dtype, shape=shape),
         root=SNode(), i="i", j="j", k="k", l="l", ij="ij", ijk="ijk", ijkl="ijkl",
         cast=cast, abs=ti_abs, sqrt=ti_sqrt, round=ti_round, floor=ti_floor,
@@ -521,6 +618,13 @@ class _AtomicRewriter(ast.NodeTransformer):
     def _is_atomic(call):
         return (isinstance(call, ast.Call) and isinstance(call.func, ast.Attribute) and call.func.attr == "atomic_add" and
                 isinstance(call.func.value, ast.Name) and call.func.value.id == "ti")
+
+    def visit_Call(self, node):
+        self.generic_visit(node)
+        if self._is_atomic(node) and isinstance(node.args[0], ast.Subscript):  # works in any expression position
+            tgt = node.args[0]
+            return ast.Call(func=ast.Name(id="emu_atomic_add_", ctx=ast.Load()), args=[tgt.value, tgt.slice, node.args[1]], keywords=[])
+        return node
 
     def visit_Assign(self, node):
         self.generic_visit(node)
@@ -551,7 +655,7 @@ class _RefLoader(importlib.machinery.SourceFileLoader):
     def source_to_code(self, data, path, *, _optimize=-1):
         tree = ast.parse(data, filename=path)
         tree = _AtomicRewriter().visit(tree)
-        tree.body.insert(0, ast.parse("from oracle.taichi_emu import ti_range as range").body[0])
+        tree.body.insert(0, ast.parse("from oracle.taichi_emu import ti_range as range, emu_atomic_add_").body[0])
         ast.fix_missing_locations(tree)
         return compile(tree, path, "exec", dont_inherit=True, optimize=_optimize)
 
@@ -600,7 +704,7 @@ def load_reference(root="/root/reference"):
     sub.__path__ = [os.path.join(root, "taichi_slam", "mapping")]
     sys.modules["taichi_slam.mapping"] = sub
     mods = {}
-    for name in ("mapping_common", "dense_tsdf", "taichi_octomap", "marching_cube_mesher"):
+    for name in ("mapping_common", "dense_tsdf", "taichi_octomap", "marching_cube_mesher", "topo_graph"):
         mod = importlib.import_module("taichi_slam.mapping." + name)
         if hasattr(mod, "sign"):
             mod.sign = ti_sign

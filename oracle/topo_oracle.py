@@ -1,6 +1,9 @@
-"""CPU oracle of TopoGraphGen - TEST INFRASTRUCTURE ONLY (imported by tests/ only).  PARITY UNPINNED: the
-reference (taichi_slam/mapping/topo_graph.py) needs Taichi, which cannot run here; it ships no test with assertions
-for this class (tests/gen_topo_graph.py is a visual smoke script).
+"""CPU oracle of TopoGraphGen - TEST INFRASTRUCTURE ONLY (imported by tests/ only).  The reference
+(taichi_slam/mapping/topo_graph.py) needs Taichi, which cannot run here, and ships no test with assertions for this
+class (tests/gen_topo_graph.py is a visual smoke script).  Pinned instead by the reference's own source EXECUTED through
+oracle/taichi_emu.py: `tools/make_golden_ref.py topo` records the graph topo_graph.py builds on the two-room world,
+tests/test_topo_cpu.py::test_topo_graph_matches_executed_reference checks this restatement (and the product class)
+against it - nodes, facelets, frontier flags, projections, edges.
 
 A literal, loop-by-loop restatement of the reference in scalar float32 Python: every method cites the lines it
 follows.  `mapping` is any object with the scalar map queries of BaseMap (mapping_common.py:165-204):

@@ -82,8 +82,8 @@ def test_topo_graph_two_rooms_matches_literal_oracle():
     nr = ref.generate_topo_graph(START_A, max_nodes=12)
     assert n == nr >= 2, (n, nr)
     graphs_equal(t, ref)
-    # the graph reaches room B through the doorway: some node centre lies beyond the wall (x > 3.7 m)
-    assert max(nd["center"][0] for nd in t.nodes) > 3.7
+    # the graph reaches room B through the doorway: some node centre lies beyond the wall between the rooms (x > 0.45 m)
+    assert max(nd["center"][0] for nd in t.nodes) > 0.45
     # every polyhedron is a closed triangulated surface: each facelet has three neighbours inside its own node
     nf = t.num_facelets[None]
     assert nf == sum(nd["end"] - nd["start"] for nd in t.nodes) and nf % 2 == 0
@@ -111,3 +111,52 @@ def test_base_map_query_surface():
     assert m.is_near_pos_occupy(START_A, 0) is False  # range(-0, 0) is empty (mapping_common.py:198)
     with pytest.raises(NotImplementedError):
         BaseMap(0.05).raycast(START_A, START_A, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Against the REFERENCE'S TopoGraphGen, executed (tests/golden/ref_exec_topo.npz: topo_graph.py run unmodified through
+# oracle/taichi_emu.py on this same world by `tools/make_golden_ref.py topo`): both the literal restatement and the
+# product class must reproduce its graph.
+# ---------------------------------------------------------------------------------------------------------------
+import os
+
+TOPO_GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_topo.npz"))
+
+
+def matches_executed_reference(tag, n_nodes, n_facelets, n_frontiers, n_edge_pts, node_center, node_range, normals, is_frontier,
+                               tri, fr_valid, fr_proj, fr_next, edges):
+    g = TOPO_GOLD
+    assert [n_nodes, n_facelets, n_frontiers, n_edge_pts] == list(g[tag + "_counts"])
+    assert np.allclose(node_center, g[tag + "_node_center"], atol=1e-5)
+    assert np.array_equal(np.asarray(node_range), g[tag + "_node_range"])
+    assert np.allclose(normals, g[tag + "_facelet_normal"], atol=1e-4)
+    assert np.array_equal(np.asarray(is_frontier).astype(np.int8), g[tag + "_facelet_frontier"])
+    assert np.allclose(tri, g[tag + "_tri_vertices"], atol=1e-5)
+    assert np.array_equal(np.asarray(fr_valid).astype(np.int8), g[tag + "_frontier_valid"])
+    assert np.allclose(fr_proj, g[tag + "_frontier_proj_center"], atol=1e-5)
+    assert np.allclose(fr_next, g[tag + "_frontier_next"], atol=1e-5)
+    e, er = np.asarray(edges).reshape(-1, 6), g[tag + "_edges"].reshape(-1, 6)
+    assert np.allclose(e[np.lexsort(e.T[::-1])], er[np.lexsort(er.T[::-1])], atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,kw", [("a", dict(coll_det_num=64, max_raycast_dist=2.5)), ("b", dict(coll_det_num=128, max_raycast_dist=2))])
+def test_topo_graph_matches_executed_reference(tag, kw):
+    o = make_world()
+    # the literal restatement
+    ref = TopoOracle(ScalarOracleMap(o), **kw)
+    n = ref.generate_topo_graph(START_A, max_nodes=12)
+    matches_executed_reference(
+        tag, n, len(ref.facelets), ref.num_frontiers, 2 * len(ref.edges), [nd["center"] for nd in ref.nodes],
+        [[nd["start"], nd["end"], nd["master_idx"]] for nd in ref.nodes], [f.normal for f in ref.facelets],
+        [f.is_frontier for f in ref.facelets], np.concatenate([[f.v0, f.v1, f.v2] for f in ref.facelets]),
+        [ref.frontiers[k]["is_valid"] for k in range(ref.num_frontiers)], [ref.frontiers[k]["projected_center"] for k in range(ref.num_frontiers)],
+        [ref.frontiers[k]["next_node_initial"] for k in range(ref.num_frontiers)], [np.concatenate(p) for p in ref.edges])
+    # the product class on the oracle-backed map
+    t = TopoGraphGen(OracleBackedMap(o), **kw)
+    n = t.generate_topo_graph(START_A, max_nodes=12)
+    nf, nfr = t.num_facelets[None], t.num_frontiers[None]
+    matches_executed_reference(
+        tag, n, nf, nfr, t.edge_num[None], [nd["center"] for nd in t.nodes], [[nd["start"], nd["end"], nd["master_idx"]] for nd in t.nodes],
+        t.f_normal.a[:nf], t.f_is_frontier.a[:nf], t.tri_vertices.to_numpy()[:3 * nf], [t.frontiers[k]["is_valid"] for k in range(nfr)],
+        [t.frontiers[k]["projected_center"] for k in range(nfr)], [t.frontiers[k]["next_node_initial"] for k in range(nfr)],
+        t.edges.to_numpy()[:t.edge_num[None]])

@@ -164,5 +164,34 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
+def topo():
+    """TopoGraphGen (topo_graph.py:128-511) executed on the analytic two-room world of tests/topo_world.py."""
+    ref = emu.load_reference()
+    from topo_world import two_rooms, START_A
+    idx, t, w, occ = two_rooms()
+    m = ref.dense_tsdf.DenseTSDF(map_scale=[12.8, 12.8], voxel_scale=0.05, num_voxel_per_blk_axis=16, is_global_map=True,
+                                 max_disp_particles=1024, max_submap_num=4)
+    m.load_numpy(0, idx, t, w, occ, np.array([]))
+    g = {}
+    for tag, kw in (("a", dict(coll_det_num=64, max_raycast_dist=2.5)), ("b", dict(coll_det_num=128, max_raycast_dist=2))):
+        tg = ref.topo_graph.TopoGraphGen(m, max_facelets=8192, **kw)
+        n = tg.generate_topo_graph(START_A, max_nodes=12)
+        nf, nfr, ne = tg.num_facelets[None], tg.num_frontiers[None], tg.edge_num[None]
+        g[tag + "_counts"] = np.array([n, nf, nfr, ne])
+        g[tag + "_node_center"] = np.array([tg.nodes[i].center.a for i in range(n)], np.float32)
+        g[tag + "_node_range"] = np.array([[tg.nodes[i].start_facelet_idx, tg.nodes[i].end_facelet_idx, tg.nodes[i].master_idx] for i in range(n)])
+        g[tag + "_facelet_normal"] = np.array([tg.facelets[i].normal.a for i in range(nf)], np.float32)
+        g[tag + "_facelet_frontier"] = np.array([int(tg.facelets[i].is_frontier) for i in range(nf)], np.int8)
+        g[tag + "_tri_vertices"] = tg.tri_vertices.to_numpy()[:3 * nf].astype(np.float32)
+        g[tag + "_frontier_valid"] = np.array([int(tg.frontiers[k].is_valid) for k in range(nfr)], np.int8)
+        g[tag + "_frontier_proj_center"] = np.array([tg.frontiers[k].projected_center.a for k in range(nfr)], np.float32)
+        g[tag + "_frontier_next"] = np.array([tg.frontiers[k].next_node_initial.a for k in range(nfr)], np.float32)
+        g[tag + "_edges"] = tg.edges.to_numpy()[:ne].astype(np.float32)
+        print(tag, "nodes", n, "facelets", nf, "frontiers", nfr, "edge points", ne)
+    out = os.path.join(ROOT, "tests", "golden", "ref_exec_topo.npz")
+    np.savez_compressed(out, **g)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    topo() if (len(sys.argv) > 1 and sys.argv[1] == "topo") else main()

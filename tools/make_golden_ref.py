@@ -100,6 +100,23 @@ def main():
         g["C_" + n] = a
     print(f"C {len(g['C_idx'])} voxels, {time.time() - t00:.0f}s")
 
+    # D. texture (:204-213, :233-234, :268-269): uniformly coloured images, so that the racy "last ray wins" overwrite has
+    #    one possible outcome - frame 1 in colour A everywhere, frame 2 (left half of the image valid) in colour B
+    mt = D(is_global_map=True, texture_enabled=True, **kw)
+    mt.set_dep_camera_intrinsic(K)
+    mt.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    texA = np.zeros(d1.shape + (3,), np.uint8); texA[:] = (200, 40, 90)
+    texB = np.zeros(d1.shape + (3,), np.uint8); texB[:] = (10, 250, 30)
+    mt.recast_depth_to_map(P1[0], P1[1], d1, texA)
+    d1half = d1.copy(); d1half[:, d1.shape[1] // 2:] = 0
+    mt.recast_depth_to_map(P1[0], P1[1], d1half, texB)
+    keys = sorted(k for k, v in mt.TSDF_observed.d.items() if v > 0)
+    g["D_idx"] = np.array([k[1:] for k in keys], np.int16)
+    g["D_W"] = np.array([mt.W_TSDF.d[k] for k in keys], np.float16)
+    g["D_color"] = np.array([mt.color.d[k] for k in keys], np.float16)
+    g["D_texA"], g["D_texB"], g["D_d1half"] = texA[0, 0], texB[0, 0], d1half
+    print(f"D textured {len(keys)} voxels, {time.time() - t00:.0f}s")
+
     # E. submap collection + fusion into a global map (:272-318)
     from util import rot_xyz
     sub = D(is_global_map=False, **kw)

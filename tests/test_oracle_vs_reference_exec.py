@@ -69,6 +69,15 @@ def test_depth_integration_two_frames(mode):
     assert n1 > 90000 and n2 > n1
 
 
+def test_depth_kernel_edge_semantics():
+    """recast_step 3 on a 119 x 157 image (range(0, h/step) truncates), zero / too-far / too-near pixels skipped (:196-199),
+    internal_voxels 5."""
+    o = OracleTSDF(K=list(G["K"]), is_global_map=True, mode=MODE_F16_FAITHFUL, recast_step=3, internal_voxels=5, **KW)
+    R, T = f32pose(G["P2_R"], G["P2_T"])
+    o.integrate_depth(R, T, G["B_depth"])
+    assert compare_state(o, "B") > 20000
+
+
 @pytest.mark.parametrize("mode", [MODE_F16_FAITHFUL, MODE_CANONICAL])
 def test_point_cloud_integration(mode):
     o = OracleTSDF(is_global_map=True, mode=mode, **KW)

@@ -92,6 +92,21 @@ def main():
         g["A2_" + n] = a
     print(f"A2 {len(g['A2_idx'])} voxels, {time.time() - t00:.0f}s")
 
+    # B. edge semantics of the depth kernel (:188-203): image size not a multiple of recast_step (range(0, h/step) truncates),
+    #    zero pixels, pixels beyond max_ray_length*1000 and below min_ray_length*1000, a different internal_voxels
+    dB = d1[:119, :157].copy()
+    dB[::7, ::5] = 0
+    dB[3::11, 2::13] = 3500        # > max_ray_length * 1000
+    dB[5::13, 1::11] = 250         # < min_ray_length * 1000
+    mB = D(is_global_map=True, recast_step=3, internal_voxels=5, **kw)
+    mB.set_dep_camera_intrinsic(K)
+    mB.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    mB.recast_depth_to_map(P2[0], P2[1], dB, e)
+    for n, a in zip(("idx", "T", "W", "occ", "occcells"), state(mB)):
+        g["B_" + n] = a
+    g["B_depth"] = dB
+    print(f"B {len(g['B_idx'])} voxels, {time.time() - t00:.0f}s")
+
     # C. point-cloud variant (:167-186)
     m = D(is_global_map=True, **kw)
     m.set_base_pose_submap(0, np.eye(3), np.zeros(3))

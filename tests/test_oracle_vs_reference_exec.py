@@ -102,6 +102,16 @@ def test_exporters_and_io_roundtrip():
     ref = G["F_surface_xyz"]
     assert ns == len(ref)
     assert np.allclose(xyz[np.lexsort(xyz.T[::-1])], ref[np.lexsort(ref.T[::-1])], atol=1e-6)
+    # slice export (:367-389): the layer k == int(f16(z)/vs) for dz = 0.5, three layers for dz = 1.5
+    for tag in ("s1", "s3"):
+        z, dz = G[f"F_{tag}_z_dz"]
+        n2, sxyz, sval = o.slice(float(z), float(dz))
+        rxyz, rval = G[f"F_{tag}_xyz"], G[f"F_{tag}_val"]
+        assert n2 == len(rxyz) > 100
+        a_, b_ = np.lexsort(sxyz.T[::-1]), np.lexsort(rxyz.T[::-1])
+        assert np.allclose(sxyz[a_], rxyz[b_], atol=1e-6) and np.array_equal(sval[a_], rval[b_])
+    # append mode (cvt_TSDF_surface_to_voxels_to): the counter keeps running from its previous value
+    assert int(G["F_append_count"]) == 7 + ns
 
 
 def test_marching_cubes_on_reference_state():

@@ -79,6 +79,17 @@ def main():
     ns = int(m2.num_TSDF_particles[None])
     g["F_surface_xyz"] = m2.export_TSDF_xyz.to_numpy()[:ns].astype(np.float32)
     g["F_loaded_count"] = np.array(int(m2.count_active()))
+    # slice export (:367-389): k index == int(f16(z) / vs) for dz = 0.5; then dz = 1.5 (three layers)
+    for tag, z, dz in (("s1", 0.52, 0.5), ("s3", 0.33, 1.5)):
+        m2.cvt_TSDF_to_voxels_slice(z, dz)
+        nsl = int(m2.num_TSDF_particles[None])
+        g[f"F_{tag}_xyz"] = m2.export_TSDF_xyz.to_numpy()[:nsl].astype(np.float32)
+        g[f"F_{tag}_val"] = m2.export_TSDF.to_numpy()[:nsl].astype(np.float32)
+        g[f"F_{tag}_z_dz"] = np.array([z, dz])
+    # append mode of the surface export (cvt_TSDF_surface_to_voxels_to, :326-328): counter keeps running
+    m2.num_TSDF_particles[None] = 7
+    m2.cvt_TSDF_surface_to_voxels_to(m2.num_TSDF_particles, m2.max_disp_particles, m2.export_TSDF_xyz, m2.export_color)
+    g["F_append_count"] = np.array(int(m2.num_TSDF_particles[None]))
     # H. marching cubes on the loaded map (marching_cube_mesher.py:127-187), step 1
     mesher = MC(m2, max_triangles=200000, tsdf_surface_thres=0.1)
     mesher.generate_mesh(1)

@@ -487,8 +487,10 @@ def cast(v, dt):
 
 
 def _round_half_away(a):
+    """llvm.round: nearest integer, halves away from zero - exact (|a| + 0.5 would round 0.49999997 up in f32)."""
     a = np.asarray(a, dtype=np.float32)
-    return np.copysign(np.floor(np.abs(a) + np.float32(0.5)), a)  # llvm.round
+    t = np.trunc(a)
+    return np.where(np.abs(a - t) >= np.float32(0.5), t + np.copysign(np.float32(1.0), a), t).astype(np.float32)
 
 
 def ti_round(v, dt=None):

@@ -236,5 +236,30 @@ def topo():
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
+def f32_state():
+    """The reference's integrate kernels with every `ti.f16` declaration read as `ti.f32` (same algorithm, f32 state): what
+    the f32-state modes of the oracle - and with them the CUDA path - should reproduce without the f16 noise."""
+    emu.f16.np = np.float32
+    ref = emu.load_reference()
+    K, d1, d2, P1, P2, pcl = inputs()
+    g = {}
+    m = ref.dense_tsdf.DenseTSDF(is_global_map=True, map_scale=[6.4, 6.4], voxel_scale=0.05, num_voxel_per_blk_axis=16,
+                                 max_ray_length=3.0, max_disp_particles=4096, max_submap_num=4)
+    m.set_dep_camera_intrinsic(K)
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    e = np.array([])
+    for tag, (P, d) in (("A1", (P1, d1)), ("A2", (P2, d2))):
+        m.recast_depth_to_map(P[0], P[1], d, e)
+        keys = sorted(k for k, v in m.TSDF_observed.d.items() if v > 0)
+        g[tag + "_idx"] = np.array([k[1:] for k in keys], np.int16)
+        g[tag + "_T"] = np.array([m.TSDF.d[k] for k in keys], np.float32)
+        g[tag + "_W"] = np.array([m.W_TSDF.d[k] for k in keys], np.float32)
+        print(tag, len(keys), "voxels")
+    out = os.path.join(ROOT, "tests", "golden", "ref_exec_f32.npz")
+    np.savez_compressed(out, **g)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
-    topo() if (len(sys.argv) > 1 and sys.argv[1] == "topo") else main()
+    mode = sys.argv[1] if len(sys.argv) > 1 else ""
+    {"topo": topo, "f32": f32_state}.get(mode, main)()

@@ -246,3 +246,42 @@ def test_f32_state_modes_equal_the_reference_run_with_f32_fields(mode):
         else:
             # a sample on a rounding boundary may land in the neighbouring voxel (exact vs f32 bucket means differ by an ulp)
             assert np.percentile(dt, 99.9) <= 2e-5 and np.percentile(dw, 99.9) <= 1e-5 and dt.max() <= 0.05, (tag, np.percentile(dt, 99.9), dt.max())
+
+
+def test_f32_state_marching_cubes_and_fusion():
+    """Same f32-state run: marching cubes on the integrated map and submap fusion, compared without any f16 allowance."""
+    from scipy.spatial import cKDTree
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_f32.npz"))
+    # marching cubes: scatter the reference's f32 state into the oracle, mesh, compare vertices and normals
+    o = OracleTSDF(is_global_map=True, **KW)
+    o.scatter(0, g["A1_idx"].astype(np.int32), g["A1_T"], g["A1_W"], np.zeros(len(g["A1_T"]), np.int8))
+    nt, v, nrm = o.marching_cubes(1, 0.1)
+    ref_v, ref_n = g["A1_mc_vertices"].reshape(-1, 9), g["A1_mc_normals"].reshape(-1, 9)
+    assert nt == len(ref_v) > 100
+    a = v.reshape(-1, 9).astype(np.float64)
+    d_ab, j = cKDTree(ref_v.astype(np.float64)).query(a)
+    d_ba, _ = cKDTree(a).query(ref_v.astype(np.float64))
+    assert d_ab.max() <= 1e-6 and d_ba.max() <= 1e-6, (d_ab.max(), d_ba.max())
+    fin = np.isfinite(ref_n[j]).all(1) & np.isfinite(nrm.reshape(-1, 9)).all(1)
+    assert fin.mean() > 0.9 and np.abs(ref_n[j][fin] - nrm.reshape(-1, 9)[fin]).max() <= 1e-5
+    # fusion
+    sub = OracleTSDF(K=list(G["E_K"]), is_global_map=False, mode=1, **KW)
+    glo = OracleTSDF(is_global_map=True, mode=1, **dict(KW, map_scale=[12.8, 12.8]))
+    for s in range(2):
+        Rb, Tb = G["E_base_R"][s], G["E_base_T"][s]
+        Rw, Tw = Rb @ G["P1_R"], Rb @ G["P1_T"] + Tb
+        Ri, Ti = f32pose(Rb.T @ Rw, Rb.T @ (Tw - Tb))
+        for m in (sub, glo):
+            m.set_submap_pose(s, Rb, Tb)
+        sub.integrate_depth(Ri, Ti, G["E_dsmall"], submap=s)
+    glo.fuse_from(sub)
+    gi, gt, gw, go = glo.gather(0)
+    ri = g["E_glo_idx"].astype(np.int32)
+    assert set(map(tuple, ri)) == set(map(tuple, gi))
+    kg, kr = key_sort(gi), key_sort(ri)
+    rt, rw = g["E_glo_T"][kr], g["E_glo_W"][kr]
+    assert np.array_equal(np.isfinite(rt), np.isfinite(gt[kg]))
+    fin = np.isfinite(rt)
+    # sequential weighted mean, thousands of corner splats per voxel in a different (block) order: f32 rounding only
+    assert np.abs(gt[kg][fin] - rt[fin]).max() <= 2e-4 and np.percentile(np.abs(gt[kg][fin] - rt[fin]), 99) <= 2e-5
+    assert np.all(np.abs(gw[kg][fin] - rw[fin]) <= 1e-4 * np.maximum(1.0, rw[fin]))

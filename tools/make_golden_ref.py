@@ -255,6 +255,33 @@ def f32_state():
         g[tag + "_T"] = np.array([m.TSDF.d[k] for k in keys], np.float32)
         g[tag + "_W"] = np.array([m.W_TSDF.d[k] for k in keys], np.float32)
         print(tag, len(keys), "voxels")
+        if tag == "A1":   # marching cubes straight on the f32 map (marching_cube_mesher.py:127-187)
+            mesher = ref.marching_cube_mesher.MarchingCubeMesher(m, max_triangles=100000, tsdf_surface_thres=0.1)
+            mesher.generate_mesh(1)
+            nt = int(mesher.num_facelets[None])
+            g["A1_mc_vertices"] = mesher.mesh_vertices.to_numpy()[:3 * nt].astype(np.float32)
+            g["A1_mc_normals"] = mesher.mesh_normals.to_numpy()[:3 * nt].astype(np.float32)
+            print("   triangles", nt)
+    # submaps + fusion with f32 state (dense_tsdf.py:272-318)
+    from util import rot_xyz
+    kw = dict(map_scale=[6.4, 6.4], voxel_scale=0.05, num_voxel_per_blk_axis=16, max_ray_length=3.0, max_disp_particles=4096, max_submap_num=4)
+    sub = ref.dense_tsdf.DenseTSDF(is_global_map=False, **kw)
+    glo = ref.dense_tsdf.DenseTSDF(is_global_map=True, **dict(kw, map_scale=[12.8, 12.8]))
+    base = [(rot_xyz(0.1, 0.2, 0.3), np.array([0.5, 0.1, -0.2])), (rot_xyz(-0.3, 0.1, 1.0), np.array([-0.4, 0.6, 0.3]))]
+    dsmall = d1[::2, ::2].copy()
+    sub.set_dep_camera_intrinsic([v / 2 if i in (0, 2, 4, 5) else v for i, v in enumerate(K)])
+    for s_, (Rb, Tb) in enumerate(base):
+        sub.set_base_pose_submap(s_, Rb, Tb)
+        glo.set_base_pose_submap(s_, Rb, Tb)
+        sub.recast_depth_to_map(Rb @ P1[0], Rb @ P1[1] + Tb, dsmall, e)
+        if s_ == 0:
+            sub.switch_to_next_submap()
+    glo.fuse_submaps(sub)
+    keys = sorted(k for k, v in glo.TSDF_observed.d.items() if v > 0)
+    g["E_glo_idx"] = np.array([k[1:] for k in keys], np.int16)
+    g["E_glo_T"] = np.array([glo.TSDF.d[k] for k in keys], np.float32)
+    g["E_glo_W"] = np.array([glo.W_TSDF.d[k] for k in keys], np.float32)
+    print("fused", len(keys), "voxels")
     out = os.path.join(ROOT, "tests", "golden", "ref_exec_f32.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

@@ -358,7 +358,7 @@ class Field:
         return iter(sorted(ks))
 
     def parent(self, n=1):
-        if n != 1:
+        if n not in (0, 1):  # 0: the field's own node, 1: its innermost container - one cell per element either way
             raise NotImplementedError("taichi_emu: struct-for over ancestor SNodes (level-of-detail export) is not emulated")
         return self
 

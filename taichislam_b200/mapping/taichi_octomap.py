@@ -96,12 +96,20 @@ class Octomap(BaseMap):
         self._h.integrate_depth(np.asarray(depthmap), self.input_R_np, self.input_T_np, submap=self._active(), texture=tex)
 
     # :90-114
+    @staticmethod
+    def _lod(level):
+        """`occupy.parent(level)` (:95): level 0 is the field's own node, level 1 the innermost pointer node - one cell per
+        voxel either way (the node runs with disp_level = 0, taichislam_node.py:37); level L > 1 = K^(L-1)-voxel groups."""
+        return max(int(level), 1)
+
     def cvt_occupy_to_voxels(self, level):
+        level = self._lod(level)
         self.num_export_particles.t.zero_()
         self._h.extract(self._active(), level, self.export_x.t, self.num_export_particles.t,
                         self.export_color.t if self.enable_texture else None)  # :101-102
 
     def cvt_occupy_voxels_to(self, level, cur_num, max_disp_particles, x, color):
+        level = self._lod(level)
         self._h.extract(self._active(), level, x.t[:max_disp_particles], cur_num.t,
                         color.t[:max_disp_particles] if self.enable_texture else None)  # :113-114
 

@@ -291,6 +291,18 @@ class DenseTSDF(BaseMap):
         self._flush()
         return self._h.query_near_occupy(xyz, voxel, submap=self._active())
 
+    def init_sphere(self):
+        """dense_tsdf.py:136-146 as intended by tests/marching_cube_test.py:20-21: an analytic sphere SDF of radius
+        3 voxels in a 30^3 region (the reference indexes its 4-D fields with three indices there and uses uncentred
+        coordinates, so the kernel does not run at HEAD; this is the centred, working form: TSDF = |p| - radius)."""
+        r = np.arange(-15, 15)
+        I, J, K = np.meshgrid(r, r, r, indexing="ij")
+        idx = np.stack([I.ravel(), J.ravel(), K.ravel()], 1).astype(np.int32)
+        p = idx.astype(np.float32) * np.float32(self.voxel_scale)
+        t = np.sqrt((p * p).sum(1)).astype(np.float32) - np.float32(self.voxel_scale * 3)
+        self.load_numpy(self._active(), idx, t, np.ones_like(t), np.zeros(len(t), np.int8),
+                        np.full((len(t), 3), 0.5, np.float32) if self.enable_texture else np.array([]))
+
     # ------------------------------------------------------------------ extras (not in the reference)
     def frame_counters(self):
         """Flush, commit and read the integrate counters back (bench.py end-to-end arm)."""

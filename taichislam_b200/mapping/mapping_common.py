@@ -15,6 +15,23 @@ def sign(val):  # mapping_common.py:5-7
     return (0 < val) - (val < 0)
 
 
+class _ZeroD:
+    """`field[None]` face of a 0-d Taichi field over a host array: TaichiSLAM_demo.py:44-48 writes the pose straight into
+    `mapping.input_T[None][i]` / `mapping.input_R[None][i, j]` - the writes land in the buffers handed to the C ABI."""
+
+    def __init__(self, a):
+        self._a = a
+
+    def __getitem__(self, idx):
+        return self._a
+
+    def __setitem__(self, idx, v):
+        self._a[...] = v
+
+    def to_numpy(self):
+        return self._a.copy()
+
+
 class BaseMap:
     def __init__(self, voxel_scale):
         self.base_T_np = np.zeros(3)          # :16-17
@@ -22,6 +39,7 @@ class BaseMap:
         self.input_R_np = np.eye(3, dtype=np.float32)   # input_R / input_T 0-d fields (:12-13), kept on the host
         self.input_T_np = np.zeros(3, dtype=np.float32)
         self._pose_tmp_R, self._pose_tmp_d, self._pose_tmp_T = np.zeros((3, 3)), np.zeros(3), np.zeros(3)
+        self.input_R, self.input_T = _ZeroD(self.input_R_np), _ZeroD(self.input_T_np)   # mapping_common.py:12-13
         self.frame_id = 0
         self.submap_enabled = False
         self.voxel_scale = voxel_scale

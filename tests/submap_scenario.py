@@ -26,7 +26,8 @@ class Recorder:
 
     NAMES = ["recast_depth_to_map", "recast_pcl_to_map", "fuse_submaps", "export_submap", "saveMap", "set_base_pose_submap",
              "switch_to_next_submap", "get_active_submap_id", "input_remote_submap", "cvt_TSDF_surface_to_voxels",
-             "cvt_TSDF_surface_to_voxels_to", "cvt_TSDF_to_voxels_slice", "set_dep_camera_intrinsic", "set_color_camera_intrinsic"]
+             "cvt_TSDF_surface_to_voxels_to", "cvt_TSDF_to_voxels_slice", "set_dep_camera_intrinsic", "set_color_camera_intrinsic",
+             "cvt_occupy_to_voxels", "cvt_occupy_voxels_to"]
 
     def __init__(self):
         self.trace = []
@@ -82,6 +83,12 @@ class Recorder:
         def cvt_TSDF_to_voxels_slice(m, z, *a, **k):
             rec.trace.append([rec.role(m), "cvt_TSDF_to_voxels_slice", float(z).hex()])
 
+        def cvt_occupy_to_voxels(m, level=None):
+            rec.trace.append([rec.role(m), "cvt_occupy_to_voxels", None if level is None else int(level)])
+
+        def cvt_occupy_voxels_to(m, level, cur_num, max_disp, x, color):
+            rec.trace.append([rec.role(m), "cvt_occupy_voxels_to", int(level), int(max_disp)])
+
         def set_dep_camera_intrinsic(m, K):
             rec.trace.append([rec.role(m), "set_dep_camera_intrinsic", hexes(K)])
 
@@ -89,11 +96,12 @@ class Recorder:
             rec.trace.append([rec.role(m), "set_color_camera_intrinsic", hexes(K)])
 
         loc = locals()
-        return [mock.patch.object(cls, n, loc[n]) for n in self.NAMES]
+        return [mock.patch.object(cls, n, loc[n], create=True) for n in self.NAMES]
 
 
-def run(SubmapMapping, DenseTSDF, rec):
-    """The session.  Returns nothing; everything of interest is in rec.trace."""
+def run(SubmapMapping, DenseTSDF, rec, octomap=False):
+    """The session.  Returns nothing; everything of interest is in rec.trace.  `DenseTSDF` is the map class handed to
+    SubmapMapping (the Octomap class when octomap=True)."""
     rng = np.random.default_rng(7)
     sm = SubmapMapping(DenseTSDF, keyframe_step=4, sub_opts=dict(map_scale=[6.4, 6.4], max_submap_num=16),
                        global_opts=dict(map_scale=[12.8, 12.8]))
@@ -132,8 +140,13 @@ def run(SubmapMapping, DenseTSDF, rec):
     f = io.BytesIO()
     np.save(f, sub)
     sm.input_remote_submap(zlib.compress(f.getbuffer(), level=1))
-    sm.cvt_TSDF_surface_to_voxels()
-    sm.set_exporting_local()
-    sm.cvt_TSDF_surface_to_voxels()
-    sm.cvt_TSDF_to_voxels_slice(0.5)
+    if octomap:
+        sm.cvt_occupy_to_voxels(0)
+        sm.set_exporting_local()
+        sm.cvt_occupy_to_voxels(2)
+    else:
+        sm.cvt_TSDF_surface_to_voxels()
+        sm.set_exporting_local()
+        sm.cvt_TSDF_surface_to_voxels()
+        sm.cvt_TSDF_to_voxels_slice(0.5)
     rec.trace.append(["state", "submaps", sorted((int(k), int(v)) for k, v in sm.submaps.items()), int(sm.frame_count), int(sm.last_frame_id)])

@@ -164,3 +164,32 @@ def test_submap_mapping_call_trace_matches_reference():
     assert len(got) == len(ref)
     for a, b in zip(got, ref):
         assert a == b, (a[:3], b[:3])
+
+
+def test_submap_mapping_call_trace_matches_reference_octomap():
+    """The same session with Octomap as the map class (SubmapMapping(Octomap, ...), taichislam_node.py:199-201), incl. the
+    level-of-detail export calls with display level 0 (what the node passes) and 2."""
+    import contextlib
+    import io
+    import submap_scenario as sc
+    import taichislam_b200.mapping.taichi_octomap as oc
+    import taichislam_b200.mapping.submap_mapping as smm
+    rec = sc.Recorder()
+
+    def light_init(self, map_scale=[10, 10], voxel_scale=0.05, texture_enabled=False, max_disp_particles=1000000, is_global_map=False, **kw):
+        self.is_global_map = is_global_map
+        self.enable_texture = texture_enabled
+        self.max_disp_particles = max_disp_particles
+        self.export_color = self.export_x = self.num_export_particles = object()
+
+    with contextlib.ExitStack() as st:
+        st.enter_context(mock.patch.object(oc.Octomap, "__init__", light_init))
+        for pch in rec.patches(oc.Octomap):
+            st.enter_context(pch)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sc.run(smm.SubmapMapping, oc.Octomap, rec, octomap=True)
+    ref = [e for e in HOST_GOLD["submap_mapping_trace_octomap"] if e[1] != "saveMap"]
+    got = json.loads(json.dumps([e for e in rec.trace if e[1] != "saveMap"]))
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a == b, (a[:3], b[:3])

@@ -137,6 +137,13 @@ def main():
         with contextlib.redirect_stdout(_io.StringIO()):
             sc.run(SubmapMapping, DenseTSDF, rec)
     g["submap_mapping_trace"] = rec.trace
+    rec = sc.Recorder()
+    with contextlib.ExitStack() as st:
+        for pch in rec.patches(Octomap):
+            st.enter_context(pch)
+        with contextlib.redirect_stdout(_io.StringIO()):
+            sc.run(SubmapMapping, Octomap, rec, octomap=True)
+    g["submap_mapping_trace_octomap"] = rec.trace
     json.dump(g, open(OUT, "w"), indent=0)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

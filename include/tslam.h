@@ -45,7 +45,7 @@ const char* tslam_last_error(void);
 int tslam_device_count(void);
 /* ABI version of this header (tests check the library agrees). */
 int tslam_abi_version(void);
-#define TSLAM_ABI_VERSION 2
+#define TSLAM_ABI_VERSION 3
 
 /* ----------------------------------------------------------------------------
  * TSDF map  (DenseTSDF, dense_tsdf.py)
@@ -169,6 +169,15 @@ int64_t tslam_tsdf_launch_count(tslam_tsdf_t* m);
  * i < min(n, recorded); *n_out = rows written.  Synchronises. */
 int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on);
 int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out);
+/* Same ring, 7 columns per launch: bucket, ray march (all its kernels), commit, then the ray march split into
+ * ray set-up + segment count / scan / segment fill / block march (tslam_march.cu; zeros for the legacy kernel). */
+int tslam_tsdf_kernel_ms2(tslam_tsdf_t* m, int32_t n, float* ms7, int32_t* n_out);
+/* Diagnostics of the block-binned ray march (process_new_pcl, dense_tsdf.py:236-270) since the last clear of
+ * tslam_tsdf_get_stats: out6 = segments, work items, samples that took the exact-index path (fraction within
+ * near_eps of .5), samples applied through a global reduction because their exact voxel lies outside the work
+ * item's block, samples of the generic path, fast-path indices that disagreed with the exact index
+ * (TSLAM_MARCH_VERIFY=1 only; must be 0).  Synchronises. */
+int tslam_tsdf_get_march_stats(tslam_tsdf_t* m, int64_t* out6);
 
 /* ----------------------------------------------------------------------------
  * Map queries for planners - batched forms of the @ti.func helpers of BaseMap (mapping_common.py:165-204) that

@@ -16,7 +16,7 @@ E_INVALID, E_CUDA, E_POOL_FULL, E_CAPACITY, E_NOGPU = -1, -2, -3, -4, -5
 MEM_DEVICE, MEM_HOST = 0, 1
 F_COMMIT = 1
 MAX_BATCH = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TslamError(RuntimeError):
@@ -81,6 +81,8 @@ SIGNATURES = {
     "tslam_tsdf_launch_count": (_i64, [_vp]),
     "tslam_tsdf_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tslam_tsdf_kernel_ms": (C.c_int, [_vp, _i32, _vp, C.POINTER(_i32)]),
+    "tslam_tsdf_kernel_ms2": (C.c_int, [_vp, _i32, _vp, C.POINTER(_i32)]),
+    "tslam_tsdf_get_march_stats": (C.c_int, [_vp, _vp]),
     "tslam_tsdf_query_points": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "tslam_tsdf_query_near_occupy": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "tslam_tsdf_raycast": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),

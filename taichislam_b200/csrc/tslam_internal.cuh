@@ -33,6 +33,7 @@
 #define TS_ERR_TABLE_FULL 2
 #define TS_ERR_RAYLIST_FULL 4
 #define TS_PROF_RING 512
+#define TS_PROF_EV 8   // events per profiled integrate launch
 
 struct TsGrid {
   unsigned long long* table;  // hash words
@@ -160,6 +161,50 @@ __device__ __forceinline__ int ts_get_or_alloc_cached(const G& g, unsigned long 
 }
 
 // ---------------------------------------------------------------------------
+// arithmetic helpers shared by the integrate kernels (tslam_tsdf.cu, tslam_march.cu)
+// ---------------------------------------------------------------------------
+#define WMAX 1000.0f          // dense_tsdf.py:8
+#define FIXQ 1048576.0f       // 2^20: fixed-point quantum of the per-frame bucket sums
+#define FIXQ_D 1048576.0
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int iroundf(float x) { return (int)roundf(x); }  // ti.round(x, i32) mapping_common.py:263-266
+__device__ __forceinline__ float sgnf(float v) { return (float)((0.0f < v) - (v < 0.0f)); }  // mapping_common.py:5-7
+
+// x / vs, correctly rounded, without the slow-path check of the generic IEEE division: rvs = RN(1/vs) comes
+// from the host; q1 = fma(fma(-q0, vs, x), rvs, q0) is the correctly rounded quotient (Markstein) for the
+// operand ranges that occur here (|x| < 1e4 m, vs ~ 1e-2..1 m: no overflow / underflow / denormals).
+__device__ __forceinline__ float div_vs(float x, float vs, float rvs) {
+  const float q0 = __fmul_rn(x, rvs);
+  const float e = __fmaf_rn(-q0, vs, x);
+  return __fmaf_rn(e, rvs, q0);
+}
+
+__device__ __forceinline__ void red_add_f32x2(float2* addr, float a, float b) {
+  // one 8-byte vector reduction without return value: REDG.E.ADD.F32x2 (sm_90+).  Spelled in PTX because
+  // atomicAdd(float2*) was lowered to ATOMG (response sector per update) inside the divergent march loop.
+  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+#define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
+// block lookup for the march loop: shared-memory table first (global loads queue behind the reduction traffic in
+// the in-order L1TEX pipe: measured as the top stall), hash grid on a miss.
+__device__ __forceinline__ int rm_lookup(const TsGrid& g, unsigned long long* tab, unsigned long long key, int bx, int by, int bz) {
+  const int h = ((bx & 15) << 8) | ((by & 15) << 4) | (bz & 15);
+  const unsigned long long w = tab[h];
+  if ((w >> 24) == key) return (int)(w & TS_IDX_MASK);
+  const int blk = ts_get_or_alloc_cached(g, key);
+  if (blk >= 0) {
+    ts_mark_dirty(g, blk);
+    tab[h] = (key << 24) | (unsigned long long)blk;  // benign race: any writer stores a valid word
+  }
+  return blk;
+}
+
+
+// ---------------------------------------------------------------------------
 // per-frame parameters of one integrate launch, passed BY VALUE as a
 // __grid_constant__ kernel parameter (no H2D copy, no lifetime hazards)
 // ---------------------------------------------------------------------------
@@ -200,6 +245,54 @@ struct __align__(64) TsBucket {
 
 struct TsCounters {  // device-side statistics (tslam_tsdf_get_stats)
   unsigned long long n_px, n_valid, n_rays, n_updates, n_oob;
+  // block-binned ray march (tslam_march.cu): diagnostics, not part of the parity counters
+  unsigned long long n_segs, n_items, n_slow, n_fallback, n_generic, n_verify_bad;
+};
+
+// ---------------------------------------------------------------------------
+// block-binned ray march (tslam_march.cu)
+// ---------------------------------------------------------------------------
+// One record per live ray (= per-frame bucket), written by k_ray_setup: unit direction, length, sensor origin in
+// VOXEL units (T/vs) and the ray's sample weight 1/z^2 (dense_tsdf.py:243-247,262).
+struct __align__(16) TsRay {
+  float ux, uy, uz, L;
+  float tx, ty, tz, w;
+};
+// aux word per ray: [31:16] n = number of march steps (dense_tsdf.py:249-251), [15:8] frame of the batch, [0] wide
+// (more than 65535 steps: generic path)
+#define TS_AUX_WIDE 1u
+// A segment = run of consecutive march steps of one ray whose samples fall (approximately - every sample is
+// re-checked exactly by the march kernel) into one 16^3 voxel block.  jc = j0 << 8 | count (count <= 32).
+struct TsSeg { uint32_t ray, jc; };
+// generic-list records use jc = j0 << 12 | count (count <= 4095)
+struct TsItem { int blk; uint32_t seg0, nseg, pad; };  // work item of k_march_blocks: <= MR_CHUNK segments of one block
+#define MR_CHUNK 4096
+struct TsMarchCtl {  // device-side control block of one launch (zeroed by k_march_reset at its end)
+  int n_touched;     // blocks that received at least one segment
+  int n_items;       // work items built by k_seg_scan
+  int item_cursor;   // persistent-CTA work cursor of k_march_blocks
+  int n_gen;         // generic-list records
+  int overflow;      // total segments > seg_cap: every ray goes through the generic path this launch
+  unsigned int total_segs;
+  unsigned int fmax_bits;  // float bits of max over rays of max(w, w*|ds|max): sizes the fixed-point scale of the launch
+  int scale_k;       // shared-memory sums are kept in units of 2^-scale_k (k_seg_scan: largest k with max * 2^k < 2^30)
+  int ticket;
+  int pad[3];
+};
+struct TsMarchWs {
+  TsRay* rays;         // [ray_list_cap]
+  uint32_t* aux;       // [ray_list_cap]
+  TsSeg* seg;          // [seg_cap] segments grouped by block
+  uint32_t seg_cap;
+  int* seg_count;      // [max_blocks] histogram, then fill cursor
+  uint32_t* seg_off;   // [max_blocks] start of the block's segment run
+  int* touched;        // [max_blocks]
+  TsItem* items;       // [item_cap]
+  uint32_t item_cap;
+  TsSeg* gen;          // [gen_cap] generic-path records (volume boundary, wide rays, overflow)
+  uint32_t gen_cap;
+  TsMarchCtl* ctl;
+  float near_eps;      // |frac - 0.5| below this -> exact index path
 };
 
 // host-side handle
@@ -246,6 +339,9 @@ struct tslam_tsdf {
   cudaEvent_t* ev;          // profiling ring: TS_PROF_RING launches x 4 events (created lazily)
   long long prof_launches;  // integrate launches recorded since profiling was switched on
   int sm_count;
+  TsMarchWs mw;        // block-binned ray march workspace (tslam_march.cu)
+  int march_mode;      // 0 = legacy k_raymarch, 1 = block-binned (default for untextured maps), env TSLAM_MARCH
+  int march_verify;    // TSLAM_MARCH_VERIFY=1: every fast-path index is re-computed exactly, mismatches counted
   bool clamp_on_commit;
   // frame queue of the per-frame API (tslam_tsdf_queue_depth): double-buffered device staging fed by a copy stream
   int q_n, q_buf, q_h, q_w;
@@ -333,3 +429,7 @@ int ts_cuda_fail(cudaError_t e, const char* what);
 // shared across translation units
 int ts_flush_pending(tslam_tsdf* m, cudaStream_t st);   // commit if anything is pending
 int ts_check_deferred(tslam_tsdf* m);                    // read + translate device error flags (synchronises)
+// tslam_march.cu: block-binned ray march of the rays listed in m->ray_list (replaces k_raymarch<false>)
+int ts_march_alloc(tslam_tsdf* m);
+void ts_march_free(tslam_tsdf* m);
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, cudaEvent_t* sub_ev);

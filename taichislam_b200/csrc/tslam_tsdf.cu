@@ -39,34 +39,9 @@ extern "C" int tslam_device_count(void) {
   return n;
 }
 
-#define WMAX 1000.0f          // dense_tsdf.py:8
-#define FIXQ 1048576.0f       // 2^20: fixed-point quantum of the per-frame bucket sums
-#define FIXQ_D 1048576.0
-
-// ---------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ int iroundf(float x) { return (int)roundf(x); }  // ti.round(x, i32) mapping_common.py:263-266
-__device__ __forceinline__ float sgnf(float v) { return (float)((0.0f < v) - (v < 0.0f)); }  // mapping_common.py:5-7
-
-// x / vs, correctly rounded, without the slow-path check of the generic IEEE division: rvs = RN(1/vs) comes
-// from the host; q1 = fma(fma(-q0, vs, x), rvs, q0) is the correctly rounded quotient (Markstein) for the
-// operand ranges that occur here (|x| < 1e4 m, vs ~ 1e-2..1 m: no overflow / underflow / denormals).
-__device__ __forceinline__ float div_vs(float x, float vs, float rvs) {
-  const float q0 = __fmul_rn(x, rvs);
-  const float e = __fmaf_rn(-q0, vs, x);
-  return __fmaf_rn(e, rvs, q0);
-}
-
 __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz) {
   return ((((unsigned long long)(bx + (1 << 20)) << 42) | ((unsigned long long)(by + (1 << 20)) << 21) |
            (unsigned long long)(bz + (1 << 20))) + 1ull);
-}
-
-__device__ __forceinline__ void red_add_f32x2(float2* addr, float a, float b) {
-  // one 8-byte vector reduction without return value: REDG.E.ADD.F32x2 (sm_90+).  Spelled in PTX because
-  // atomicAdd(float2*) was lowered to ATOMG (response sector per update) inside the divergent march loop.
-  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
 __device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
@@ -258,23 +233,8 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
 #define RM_WIN3 4096
 #define RM_FIX 16777216.0f   // 2^24
 #define RM_WIN_STEPS 18      // a sample >= 18 voxels from the sensor origin lies outside the +-8 voxel window on some axis
-#define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
 #define RM_SMEM (RM_WIN3 * 16 + RM_TAB * 8)
 #define RM_SMEM_TEX (RM_SMEM + RM_WIN3 * 8)  // textured maps: + one 64-bit colour word per window voxel
-
-// block lookup for the march loop: shared-memory table first (global loads queue behind the reduction traffic in
-// the in-order L1TEX pipe: measured as the top stall), hash grid on a miss.
-__device__ __forceinline__ int rm_lookup(const TsGrid& g, unsigned long long* tab, unsigned long long key, int bx, int by, int bz) {
-  const int h = ((bx & 15) << 8) | ((by & 15) << 4) | (bz & 15);
-  const unsigned long long w = tab[h];
-  if ((w >> 24) == key) return (int)(w & TS_IDX_MASK);
-  const int blk = ts_get_or_alloc_cached(g, key);
-  if (blk >= 0) {
-    ts_mark_dirty(g, blk);
-    tab[h] = (key << 24) | (unsigned long long)blk;  // benign race: any writer stores a valid word
-  }
-  return blk;
-}
 
 __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
   const unsigned int ux = (unsigned int)x;
@@ -843,6 +803,14 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   fill_jet_host(cm.data());
   TS_CUDA(cudaMalloc(&m->colormap, cm.size() * 4));
   TS_CUDA(cudaMemcpy(m->colormap, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice));
+  {
+    // ray march: block-binned shared-memory accumulation (tslam_march.cu) for untextured maps; TSLAM_MARCH=legacy
+    // keeps the round-1 kernel (one global reduction per sample) for A/B runs.  Textured maps use k_raymarch<true>.
+    const char* mm = getenv("TSLAM_MARCH");
+    m->march_mode = (m->cfg.texture_enabled || (mm && mm[0] == 'l') || m->cfg.max_ray_length / m->cfg.voxel_scale > 60000.0) ? 0 : 1;
+    m->march_verify = getenv("TSLAM_MARCH_VERIFY") != nullptr;
+    if (m->march_mode) { int rcm = ts_march_alloc(m); if (rcm) return rcm; }
+  }
   TS_CUDA(cudaFuncSetAttribute(k_raymarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
   TS_CUDA(cudaFuncSetAttribute(k_raymarch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_TEX));
   TS_CUDA(cudaFuncSetAttribute(k_commit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CM_SMEM));
@@ -867,8 +835,9 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
+  if (m->march_mode) ts_march_free(m);
   cudaFree(m->counters); cudaFree(m->pose_R); cudaFree(m->pose_T); cudaFree(m->colormap);
-  if (m->ev) { for (int i = 0; i < 4 * TS_PROF_RING; i++) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
+  if (m->ev) { for (int i = 0; i < TS_PROF_EV * TS_PROF_RING; i++) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
   delete m;
   return TSLAM_OK;
 }
@@ -1032,7 +1001,7 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
       TS_CUDA(cudaMemcpyAsync(m->tex_stage, tsrc, (size_t)nf * th * tw * 3, cudaMemcpyHostToDevice, st));
       tsrc = m->tex_stage;
     }
-    cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
+    cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
     dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
     const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
@@ -1043,7 +1012,10 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     if (m->g.cword)
       k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
                                                                      m->ray_list_cap, m->counters);
-    else
+    else if (m->march_mode) {
+      int rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
+      if (rcm) return rcm;
+    } else
       k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
                                                                                      m->ray_list_cap, m->counters);
     TS_LAUNCH_CHECK(m);
@@ -1086,7 +1058,7 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
   }
   const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
-  cudaEvent_t* pe = m->profiling ? m->ev + 4 * (m->prof_launches % TS_PROF_RING) : nullptr;
+  cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
   const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
   k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
@@ -1096,7 +1068,10 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
   if (m->g.cword)
     k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
                                                                    m->ray_list_cap, m->counters);
-  else
+  else if (m->march_mode) {
+    int rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
+    if (rcm) return rcm;
+  } else
     k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
                                                                     m->ray_list_cap, m->counters);
   TS_LAUNCH_CHECK(m);
@@ -1639,6 +1614,16 @@ extern "C" int tslam_tsdf_get_stats(tslam_tsdf_t* m, int64_t* out8, int clear) {
   return TSLAM_OK;
 }
 
+extern "C" int tslam_tsdf_get_march_stats(tslam_tsdf_t* m, int64_t* out6) {
+  if (!m || !out6) return TSLAM_E_INVALID;
+  TS_CUDA(cudaDeviceSynchronize());
+  TsCounters c;
+  TS_CUDA(cudaMemcpy(&c, m->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  out6[0] = (int64_t)c.n_segs; out6[1] = (int64_t)c.n_items; out6[2] = (int64_t)c.n_slow; out6[3] = (int64_t)c.n_fallback;
+  out6[4] = (int64_t)c.n_generic; out6[5] = (int64_t)c.n_verify_bad;
+  return TSLAM_OK;
+}
+
 extern "C" int tslam_tsdf_sync(tslam_tsdf_t* m, void* stream) {
   if (!m) return TSLAM_E_INVALID;
   TS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1650,8 +1635,8 @@ extern "C" int64_t tslam_tsdf_launch_count(tslam_tsdf_t* m) { return m ? m->laun
 extern "C" int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on) {
   if (!m) return TSLAM_E_INVALID;
   if (on && !m->ev) {
-    m->ev = new cudaEvent_t[4 * TS_PROF_RING];
-    for (int i = 0; i < 4 * TS_PROF_RING; i++) TS_CUDA(cudaEventCreate(&m->ev[i]));
+    m->ev = new cudaEvent_t[TS_PROF_EV * TS_PROF_RING];
+    for (int i = 0; i < TS_PROF_EV * TS_PROF_RING; i++) TS_CUDA(cudaEventCreate(&m->ev[i]));
   }
   m->profiling = on;
   m->prof_launches = 0;
@@ -1659,13 +1644,32 @@ extern "C" int tslam_tsdf_set_profiling(tslam_tsdf_t* m, int on) {
 }
 // ms3[3*i + {0,1,2}] = bucket / ray-march / commit(+reset) kernel time of the i-th most recent
 // recorded integrate launch, i < n (n <= TS_PROF_RING).  Returns the number of rows written in *n_out.
+// ms7[7*i + ...] = bucket, ray march (all of its kernels), commit, then the parts of the ray march: set-up + segment
+// count, scan, segment fill, march (+ generic + reset).  The last four are 0 for launches of the legacy kernel.
+extern "C" int tslam_tsdf_kernel_ms2(tslam_tsdf_t* m, int32_t n, float* ms7, int32_t* n_out) {
+  if (!m || !ms7 || !n_out || !m->ev) return TSLAM_E_INVALID;
+  TS_CUDA(cudaDeviceSynchronize());
+  long long have = m->prof_launches < TS_PROF_RING ? m->prof_launches : TS_PROF_RING;
+  if (n > have) n = (int32_t)have;
+  for (int i = 0; i < n; i++) {
+    cudaEvent_t* pe = m->ev + TS_PROF_EV * ((m->prof_launches - 1 - i) % TS_PROF_RING);
+    for (int q = 0; q < 3; q++) TS_CUDA(cudaEventElapsedTime(&ms7[7 * i + q], pe[q], pe[q + 1]));
+    for (int q = 0; q < 4; q++) ms7[7 * i + 3 + q] = 0.0f;
+    if (m->march_mode && !m->g.cword) {
+      TS_CUDA(cudaEventElapsedTime(&ms7[7 * i + 3], pe[1], pe[4]));
+      for (int q = 0; q < 3; q++) TS_CUDA(cudaEventElapsedTime(&ms7[7 * i + 4 + q], pe[4 + q], pe[5 + q]));
+    }
+  }
+  *n_out = n;
+  return TSLAM_OK;
+}
 extern "C" int tslam_tsdf_kernel_ms(tslam_tsdf_t* m, int32_t n, float* ms3, int32_t* n_out) {
   if (!m || !ms3 || !n_out || !m->ev) return TSLAM_E_INVALID;
   TS_CUDA(cudaDeviceSynchronize());
   long long have = m->prof_launches < TS_PROF_RING ? m->prof_launches : TS_PROF_RING;
   if (n > have) n = (int32_t)have;
   for (int i = 0; i < n; i++) {
-    cudaEvent_t* pe = m->ev + 4 * ((m->prof_launches - 1 - i) % TS_PROF_RING);
+    cudaEvent_t* pe = m->ev + TS_PROF_EV * ((m->prof_launches - 1 - i) % TS_PROF_RING);
     for (int q = 0; q < 3; q++) TS_CUDA(cudaEventElapsedTime(&ms3[3 * i + q], pe[q], pe[q + 1]));
   }
   *n_out = n;

@@ -305,3 +305,17 @@ class TsdfHandle:
         k = C.c_int32(0)
         capi.check(self.L.tslam_tsdf_kernel_ms(self.h, n, capi.np_ptr(o), C.byref(k)))
         return o[:k.value]
+
+    def kernel_ms2(self, n=512):
+        """[rows,7] ms: bucket, ray march (total), commit, then ray set-up+segment count, scan, segment fill, block march."""
+        o = np.zeros((n, 7), np.float32)
+        k = C.c_int32(0)
+        capi.check(self.L.tslam_tsdf_kernel_ms2(self.h, n, capi.np_ptr(o), C.byref(k)))
+        return o[:k.value]
+
+    def march_stats(self):
+        """Diagnostics of the block-binned ray march since the last stats(clear=True)."""
+        o = np.zeros(6, np.int64)
+        capi.check(self.L.tslam_tsdf_get_march_stats(self.h, capi.np_ptr(o)))
+        return dict(n_segs=int(o[0]), n_items=int(o[1]), n_slow=int(o[2]), n_fallback=int(o[3]), n_generic=int(o[4]),
+                    n_verify_bad=int(o[5]))

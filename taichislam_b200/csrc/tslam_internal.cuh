@@ -188,6 +188,13 @@ __device__ __forceinline__ void red_add_f32x2(float2* addr, float a, float b) {
   asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u32(unsigned int* addr, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 #define RM_TAB 4096          // shared block-lookup table: 16^3 entries indexed by the low 4 bits of the block coords
 // block lookup for the march loop: shared-memory table first (global loads queue behind the reduction traffic in
 // the in-order L1TEX pipe: measured as the top stall), hash grid on a miss.
@@ -233,13 +240,23 @@ struct TsIntrin {
   int same_proj;   // color_same_proj
 };
 
-// per-frame bucket entry (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z),
-// exact fixed-point sums (2^-20 m).  64-byte stride = two 32-byte sectors.
-struct __align__(64) TsBucket {
+// per-frame buckets (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z), two levels:
+//  * TsSlot  - open-addressing table per frame, 16 bytes: bucket key -> ray index (TS_RAY_PENDING until the opener
+//              has published it);
+//  * TsBucket - dense per-ray record with the exact fixed-point sums (2^-20 m), indexed frame * ray_cap_f + open order.
+struct __align__(16) TsSlot {
   unsigned long long key;  // packed (bx,by,bz)+1, 0 = empty
+  uint32_t ray;
+  uint32_t pad;
+};
+#define TS_RAY_PENDING 0xFFFFFFFFu
+#define TS_RAY_DROPPED 0xFFFFFFFEu
+struct __align__(64) TsBucket {
   long long sx, sy, sz, sd;
   int cnt;
   unsigned int cr, cg, cb;  // new_pcl_sum_color: exact integer channel sums
+  uint32_t slot;            // index of the bucket's slot (cleared by the consumer of the ray)
+  uint32_t frame;
   int pad[2];
 };
 
@@ -262,7 +279,7 @@ struct __align__(16) TsRay {
 // (more than 65535 steps: generic path)
 #define TS_AUX_WIDE 1u
 // A segment = run of consecutive march steps of one ray whose samples fall (approximately - every sample is
-// re-checked exactly by the march kernel) into one 16^3 voxel block.  jc = j0 << 8 | count (count <= 32).
+// re-checked exactly by the march kernel) into one 16^3 voxel block.  jc = frame << 24 | j0 << 8 | count (count <= 32).
 struct TsSeg { uint32_t ray, jc; };
 // generic-list records use jc = j0 << 12 | count (count <= 4095)
 struct TsItem { int blk; uint32_t seg0, nseg, pad; };  // work item of k_march_blocks: <= MR_CHUNK segments of one block
@@ -270,28 +287,37 @@ struct TsItem { int blk; uint32_t seg0, nseg, pad; };  // work item of k_march_b
 struct TsMarchCtl {  // device-side control block of one launch (zeroed by k_march_reset at its end)
   int n_touched;     // blocks that received at least one segment
   int n_items;       // work items built by k_seg_scan
+  int n_full;        // ... of which full chunks (front of the item list; the remainders sit at its back)
   int item_cursor;   // persistent-CTA work cursor of k_march_blocks
   int n_gen;         // generic-list records
-  int overflow;      // total segments > seg_cap: every ray goes through the generic path this launch
+  int overflow;      // work list did not fit: every segment goes through the generic path this launch
   unsigned int total_segs;
   unsigned int fmax_bits;  // float bits of max over rays of max(w, w*|ds|max): sizes the fixed-point scale of the launch
   int scale_k;       // shared-memory sums are kept in units of 2^-scale_k (k_seg_scan: largest k with max * 2^k < 2^30)
   int ticket;
-  int pad[3];
+  unsigned int tmp_cursor;  // next free entry of the segment-list pool
+  int pad;
 };
 struct TsMarchWs {
   TsRay* rays;         // [ray_list_cap]
   uint32_t* aux;       // [ray_list_cap]
-  TsSeg* seg;          // [seg_cap] segments grouped by block
+  TsSeg* seg;          // [seg_cap] segments grouped by block, ordered by length inside a block
   uint32_t seg_cap;
-  int* seg_count;      // [max_blocks] histogram, then fill cursor
-  uint32_t* seg_off;   // [max_blocks] start of the block's segment run
-  int* touched;        // [max_blocks]
+  TsSeg* tmp_seg;      // [seg_cap] per-CTA segment lists of k_seg_walk (chunks of 4096 entries from one pool)
+  uint32_t* tmp_key;   // [seg_cap] block * 16 + length class of the listed segment
+  int* seg_count;      // [max_blocks * 16] segments per (block, class); then the fill cursor of k_seg_place
+  uint32_t* seg_rel;   // [max_blocks * 16] start of the class inside the block's run
+  uint32_t* seg_off;   // [max_blocks] start of the block's run
+  int* touched;        // [max_blocks] blocks with segments
+  uint32_t* blk_total; // [max_blocks] segments of touched[i]
   TsItem* items;       // [item_cap]
   uint32_t item_cap;
-  TsSeg* gen;          // [gen_cap] generic-path records (volume boundary, wide rays, overflow)
+  TsSeg* gen;          // [gen_cap] generic-path records (volume boundary, over-long rays, overflow)
   uint32_t gen_cap;
   TsMarchCtl* ctl;
+  int* cta_n;          // [walk CTAs] segments in the CTA's list
+  uint32_t* cta_chunk; // [walk CTAs * 1024] first entry of the CTA's k-th list chunk
+  int walk_x_max;      // walk CTAs of a one-frame launch
   float near_eps;      // |frac - 0.5| below this -> exact index path
 };
 
@@ -303,11 +329,14 @@ struct tslam_tsdf {
   TsIntrin in;
   size_t table_cap;
   // integrate workspace
-  TsBucket* buckets;   // [TSLAM_MAX_BATCH * bucket_cap]
-  uint32_t bucket_cap; // power of two
-  uint32_t* ray_list;  // [TSLAM_MAX_BATCH * max_rays_per_frame]
+  TsSlot* slots;       // [TSLAM_MAX_BATCH * bucket_cap]
+  uint32_t bucket_cap; // slots per frame, power of two
+  TsBucket* bdata;     // [ray_list_cap] dense per-ray sums: frame f owns [f * ray_cap_f, (f + 1) * ray_cap_f)
+  uint32_t ray_cap_f;  // rays per frame (= sampled pixels: every bucket holds at least one)
+  int* n_rays_f;       // [TSLAM_MAX_BATCH] device counters: buckets opened per frame of the launch
+  uint32_t* ray_list;  // [ray_list_cap] compact list of ray indices (legacy / textured march only)
   uint32_t ray_list_cap;
-  int* n_rays;         // device counter
+  int* n_rays;         // device counter of ray_list
   uint16_t* depth_stage;  // device staging for host depth input [TSLAM_MAX_BATCH * max_image_pixels]
   uint8_t* tex_stage;     // device staging for host textures [2 * TSLAM_MAX_BATCH * max_image_pixels * 3] (texture_enabled only)
   uint8_t* rgb_stage;     // device staging for point-cloud colours
@@ -432,4 +461,4 @@ int ts_check_deferred(tslam_tsdf* m);                    // read + translate dev
 // tslam_march.cu: block-binned ray march of the rays listed in m->ray_list (replaces k_raymarch<false>)
 int ts_march_alloc(tslam_tsdf* m);
 void ts_march_free(tslam_tsdf* m);
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, cudaEvent_t* sub_ev);
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* sub_ev);

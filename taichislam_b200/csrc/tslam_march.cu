@@ -1,40 +1,41 @@
 // libtslam.so - block-binned ray march (round 2).  sm_100a.
 //
-// Replaces the one-thread-per-ray march of round 1 (k_raymarch, one 8-byte global reduction per sample: bound by
-// the L2 reduction rate, ~150 G/s, whatever the kernel did) for untextured maps.  process_new_pcl
-// (dense_tsdf.py:236-270) is split into
+// Replaces the one-thread-per-ray march of round 1 (k_raymarch: one 8-byte global reduction per sample, bound by the
+// L2 reduction rate of ~150 G/s whatever the kernel did) for untextured maps.  process_new_pcl
+// (dense_tsdf.py:236-270) becomes
 //
-//   k_ray_setup    per ray (= live bucket): exact bucket mean -> unit direction, length, weight, step count n
-//                  (:240-251), occupy flag (:248), one 32-byte ray record; then the ray is cut into SEGMENTS -
-//                  runs of consecutive steps that stay inside one 16^3 voxel block - and the segments are
-//                  counted per block (warp-aggregated histogram; blocks are activated on the way);
-//   k_seg_scan     exclusive scan of the per-block counts -> segment offsets and the work list: one item =
-//                  <= MR_CHUNK segments of one block;
-//   k_seg_fill     walks every ray again and drops its segments into their block's run;
-//   k_march_blocks persistent CTAs take work items.  The block's pending sums live in SHARED MEMORY as exact
-//                  64-bit fixed-point words (2^-24, lo/hi 32-bit halves, native ATOMS.ADD - measured 2.4-6 T
-//                  lane-atomics/s against 0.15-0.19 T/s for global reductions, tools/ubench/atoms_bench.cu);
-//                  the samples of a warp's 32 segments are flattened over the lanes (prefix sum), so ray-length
-//                  divergence costs nothing; each sample's voxel index comes from ONE fused multiply-add per
-//                  axis in block-local voxel units and is accepted only when its fractional part is at least
-//                  near_eps away from .5 - otherwise (~1e-3 of the samples) the lane recomputes
-//                  round((u*j*vs + T)/vs) exactly as the reference states it (:253-254), so voxel indices stay
-//                  bit-exact; a sample whose exact voxel is not in the item's block takes a global reduction.
-//                  At the end of the item every touched voxel is flushed with ONE coalesced REDG.ADD.F32x2 into
-//                  the block's `acc` plane (what k_commit folds into TSDF/W, :264-267).
+//   k_ray_setup    one thread per ray (= bucket, read sequentially from the dense per-ray array): exact bucket mean
+//                  -> unit direction, length, weight, step count n (:240-251), occupy flag (:248), a 32-byte record;
+//   k_seg_walk     one lane per ray: a 3-D DDA cuts the ray into SEGMENTS - runs of consecutive steps that stay in
+//                  one 16^3 voxel block - activates the blocks on the way, appends the segments to per-CTA lists and
+//                  counts them per (block, length class) with warp-aggregated reductions;
+//   k_seg_class    per touched block: class counts -> offsets inside the block's run, list of touched blocks;
+//   k_seg_scan     exclusive scan over the touched blocks -> run offsets + work items (<= MR_CHUNK segments of one
+//                  block each, full chunks first);
+//   k_seg_place    moves every listed segment to its place: a block's run is ordered by segment length;
+//   k_march_blocks persistent CTAs take work items.  The block's pending sums live in SHARED MEMORY as exact 64-bit
+//                  fixed-point words (no-return ATOMS.ADD: 2.4-6 T lane-atomics/s measured against 0.15-0.19 T/s
+//                  for global reductions, tools/ubench/atoms_bench.cu).  A warp walks 32 segments of equal length
+//                  in lock step, one per lane, ray parameters in registers.  Each sample's voxel index comes from
+//                  ONE fused multiply-add per axis in block-local voxel units and is accepted only when its
+//                  fractional part is at least near_eps away from .5 - otherwise (~2e-3 of the samples) the lane
+//                  recomputes round((u*j*vs + T)/vs) exactly as the reference states it (:253-254), so voxel
+//                  indices stay bit-exact; a sample whose exact voxel is not in the item's block takes a global
+//                  reduction.  At the end of the item every touched voxel is flushed with ONE coalesced
+//                  REDG.ADD.F32x2 into the block's `acc` plane (what k_commit folds into TSDF/W, :264-267);
 //   k_march_generic  the exact one-reduction-per-sample march for what the binned path does not take: segments
-//                  next to the volume boundary, rays whose weight leaves the fixed-point range, and everything
-//                  when the segment workspace overflows.
+//                  next to the volume boundary, rays with more than 65535 steps, workspace overflow.
 //
-// Sample value: ds = L - j*vs (the reference forms |P - x| * sign((P - x).m), :258-260, which equals it up to
+// Sample value: ds = L - j*vs (the reference forms |P - x| * sign((P - x).m), :258-260, which equals it up to the
 // f32 rounding of x: <= 3e-6 m on a 25 m map, tolerance 1e-4).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include "tslam_internal.cuh"
 
 #define FULL 0xffffffffu
 #define MS_THREADS 256
-#define MB_THREADS 512
+#define MB_THREADS 384
 #define MB_WARPS (MB_THREADS / 32)
 // shared accumulator layout: word index = x*MB_SX + y*MB_SY + z (skewed strides: consecutive samples of a ray
 // spread over the banks whatever its direction - 3.6-way average conflict vs 5.7 for x<<8|y<<4|z)
@@ -43,152 +44,39 @@
 #define MB_WORDS (15 * MB_SX + 15 * MB_SY + 16)  // 4426
 #define MB_MIN_WQ 16384                          // a ray whose weight is < 2^14 fixed-point units (relative rounding error > 3e-5)
                                                 // is applied with f32 global reductions instead
-struct MbWarp {
-  unsigned short map[1024];  // flattened sample -> (segment lane << 8 | step within the segment)
-  float4 ra[32];             // ux, uy, uz, first-sample x (block-local voxel units)
-  float4 rb[32];             // first-sample y, z, L - j0*vs, w
-  int j0[32];
-  uint32_t rid[32];
-};
-#define MB_SMEM (4 * MB_WORDS * 4 + MB_WARPS * (int)sizeof(MbWarp))
-
-__device__ __forceinline__ void lohi_add(unsigned int* lo, int* hi, int x) {
-  const unsigned int ux = (unsigned int)x;
-  const unsigned int old = atomicAdd(lo, ux);
-  const int c = (x >> 31) + ((old + ux) < old ? 1 : 0);  // sign extension + carry into the high word
-  if (c) atomicAdd(hi, c);
-}
+#define MB_SMEM (4 * MB_WORDS * 4)
+#define SEG_CLS 16                               // length classes per block: (count - 1) >> 1
 
 // ---------------------------------------------------------------------------
-// segment walk: the next run of steps [j, j+cnt) of a ray that stays in one block (approximately: fast index)
+// K2a: ray set-up (process_new_pcl :240-251): one thread per bucket -> one 32-byte ray record
 // ---------------------------------------------------------------------------
-struct RayWalk {
-  float ux, uy, uz, tx, ty, tz, iux, iuy, iuz;
-};
-__device__ __forceinline__ void walk_init(RayWalk& k, const TsRay& r) {
-  k.ux = r.ux; k.uy = r.uy; k.uz = r.uz; k.tx = r.tx; k.ty = r.ty; k.tz = r.tz;
-  k.iux = 1.0f / r.ux; k.iuy = 1.0f / r.uy; k.iuz = 1.0f / r.uz;
-}
-__device__ __forceinline__ float walk_axis(float u, float iu, float t, int b) {
-  // last parameter j for which round(t + u*j) stays in cells [16b, 16b+15]
-  if (u > 0.0f) return ((float)(16 * b + 16) - 0.5f - t) * iu;
-  if (u < 0.0f) return ((float)(16 * b) - 0.5f - t) * iu;
-  return 3.0e38f;
-}
-__device__ __forceinline__ int walk_next(const RayWalk& k, int j, int n, int& bx, int& by, int& bz) {
-  const float jf = (float)j;
-  bx = __float2int_rn(__fmaf_rn(k.ux, jf, k.tx)) >> TS_BSHIFT;
-  by = __float2int_rn(__fmaf_rn(k.uy, jf, k.ty)) >> TS_BSHIFT;
-  bz = __float2int_rn(__fmaf_rn(k.uz, jf, k.tz)) >> TS_BSHIFT;
-  const float je = fminf(fminf(walk_axis(k.ux, k.iux, k.tx, bx), walk_axis(k.uy, k.iuy, k.ty, by)), walk_axis(k.uz, k.iuz, k.tz, bz));
-  int jl = (int)ceilf(je) - 1;  // last step strictly before the crossing (a miss by one is caught per sample)
-  jl = max(jl, j);
-  jl = min(jl, min(n, j + 31));
-  return jl - j + 1;
-}
-// 0 = far outside the volume (every sample is out of bounds), 1 = block inside the block range, 2 = outside but
-// adjacent to it (a rounding-boundary sample may still be in bounds: exact path)
-__device__ __forceinline__ int block_class(const TsGrid& g, int bx, int by, int bz) {
-  const int b0 = (-g.hN) >> TS_BSHIFT, b1 = (g.N - g.hN - 1) >> TS_BSHIFT;
-  const int z0 = (-g.hNz) >> TS_BSHIFT, z1 = (g.Nz - g.hNz - 1) >> TS_BSHIFT;
-  if (bx >= b0 && bx <= b1 && by >= b0 && by <= b1 && bz >= z0 && bz <= z1) return 1;
-  if (bx >= b0 - 1 && bx <= b1 + 1 && by >= b0 - 1 && by <= b1 + 1 && bz >= z0 - 1 && bz <= z1 + 1) return 2;
-  return 0;
-}
-
-__device__ __forceinline__ void gen_append(const TsMarchWs& w, int* err, uint32_t ray, int j, int cnt) {
-  const int p = atomicAdd(&w.ctl->n_gen, 1);
-  if ((uint32_t)p < w.gen_cap) w.gen[p] = TsSeg{ray, ((uint32_t)j << 12) | (uint32_t)cnt};
-  else atomicOr(err, TS_ERR_RAYLIST_FULL);
-}
-
-// FILL = false: count segments per block (histogram + touched list);  FILL = true: write them.
-// Must be called by all 32 lanes; `live` masks lanes without a ray.
-template <bool FILL>
-__device__ __forceinline__ void walk_ray(const TsGrid& g, const TsMarchWs& w, unsigned long long* btab, bool live, const TsRay& ry,
-                                         uint32_t rid, int n, int s, bool wide, bool overflow, unsigned int& oob) {
-  RayWalk k;
-  walk_init(k, ry);
-  const uint32_t lane = threadIdx.x & 31u;
-  int j = 1;
-  while (true) {
-    const bool act = live && j <= n;
-    if (!__any_sync(FULL, act)) break;
-    int bx = 0, by = 0, bz = 0, cnt = 0, blk = -1;
-    bool binned = false;
-    if (act) {
-      cnt = walk_next(k, j, n, bx, by, bz);
-      const int cls = block_class(g, bx, by, bz);
-      if (wide || cls == 2) {
-        if (!FILL) gen_append(w, g.err, rid, j, cnt);
-      } else if (cls == 0) {
-        if (!FILL) oob += (unsigned)cnt;
-      } else {
-        blk = rm_lookup(g, btab, ts_pack_key(s, bx, by, bz), bx, by, bz);
-        binned = blk >= 0;  // < 0: pool exhausted (error flag raised, samples dropped)
-      }
-    }
-    if (FILL && overflow) {
-      if (binned) gen_append(w, g.err, rid, j, cnt);
-    } else {
-      const unsigned mb = __ballot_sync(FULL, binned);
-      if (binned) {
-        const unsigned grp = __match_any_sync(mb, blk);
-        const int leader = __ffs(grp) - 1;
-        int base = 0;
-        if ((int)lane == leader) {
-          base = atomicAdd(&w.seg_count[blk], __popc(grp));
-          if (!FILL && base == 0) w.touched[atomicAdd(&w.ctl->n_touched, 1)] = blk;
-        }
-        if (FILL) {
-          base = __shfl_sync(grp, base, leader);
-          const uint32_t pos = w.seg_off[blk] + (uint32_t)base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-          w.seg[pos] = TsSeg{rid, ((uint32_t)j << 8) | (uint32_t)cnt};
-        }
-      }
-    }
-    j += cnt;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K2a: ray set-up (process_new_pcl :240-251) + segment count
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(MS_THREADS) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* buckets,
-                                                           uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
-                                                           const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr) {
-  __shared__ unsigned long long btab[RM_TAB];
-  for (int e = threadIdx.x; e < RM_TAB; e += MS_THREADS) btab[e] = TS_EMPTY;
-  __syncthreads();
-  const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
+__global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* bdata, TsSlot* slots,
+                                                    const int* __restrict__ n_rays_f, uint32_t ray_cap_f, TsMarchWs w, TsCounters* ctr) {
+  const uint32_t f = blockIdx.y;
+  const uint32_t nme = min((uint32_t)n_rays_f[f], ray_cap_f);
   const float vs = in.vs;
-  unsigned int my_rays = 0, my_oob = 0, my_fmax = 0;
-  for (uint32_t base = blockIdx.x * MS_THREADS; base < n_rays; base += gridDim.x * MS_THREADS) {
-    const uint32_t r = base + threadIdx.x;
-    bool live = r < n_rays;
-    int cnt = 0, n = 0, s = 0;
-    long long sx = 0, sy = 0, sz = 0, sd = 0;
-    uint32_t f = 0;
-    if (live) {
-      const uint32_t id = ray_list[r];
-      f = id >> bucket_shift;
-      TsBucket* bk = &buckets[id];
-      cnt = bk->cnt;
-      sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
-      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
-      const uint4 z4 = make_uint4(0, 0, 0, 0);
-      uint4* q = reinterpret_cast<uint4*>(bk);
-      q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
-      live = cnt > 0;  // :240
-    }
+  unsigned int my_rays = 0, my_fmax = 0;
+  const TsFrame& fr = batch.f[f];
+  const int s = fr.submap;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nme; i += gridDim.x * 256) {
+    const uint32_t r = f * ray_cap_f + i;
+    TsBucket* bk = &bdata[r];
+    const int4 hd = *reinterpret_cast<const int4*>(&bk->cnt);  // cnt, cr, cg, cb
+    const longlong2 s01 = *reinterpret_cast<const longlong2*>(&bk->sx), s23 = *reinterpret_cast<const longlong2*>(&bk->sz);
+    const uint32_t slot = bk->slot;
+    const int cnt = hd.x;
+    const long long sx = s01.x, sy = s01.y, sz = s23.x, sd = s23.y;
+    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its slot back empty
+    *reinterpret_cast<uint4*>(&slots[slot]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    uint4* q = reinterpret_cast<uint4*>(bk);
+    q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
     TsRay ry;
     ry.ux = ry.uy = ry.uz = ry.L = ry.tx = ry.ty = ry.tz = ry.w = 0.0f;
+    int n = 0;
     bool wide = false;
-    float fmax = 0.0f;
-    if (live) {
+    if (cnt > 0) {  // :240
       my_rays++;
-      const TsFrame& fr = batch.f[f];
-      s = fr.submap;
       const double den = (double)cnt * FIXQ_D;
       const float mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
       const float my = (float)((double)sy / den);
@@ -202,9 +90,11 @@ __global__ void __launch_bounds__(MS_THREADS) k_ray_setup(const __grid_constant_
         // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
         const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
         if (ts_in_bounds(g, oi, oj, ok)) {
-          const int bx = oi >> TS_BSHIFT, by = oj >> TS_BSHIFT, bz = ok >> TS_BSHIFT;
-          const int blk = rm_lookup(g, btab, ts_pack_key(s, bx, by, bz), bx, by, bz);  // marks the block dirty
-          if (blk >= 0) g.occ[(size_t)blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
+          const int blk = ts_get_or_alloc_cached(g, ts_pack_key(s, oi >> TS_BSHIFT, oj >> TS_BSHIFT, ok >> TS_BSHIFT));
+          if (blk >= 0) {
+            g.occ[(size_t)blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
+            ts_mark_dirty(g, blk);  // touched blocks are listed even when only `occupy` changed
+          }
         }
         n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
         ry.w = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
@@ -213,89 +103,269 @@ __global__ void __launch_bounds__(MS_THREADS) k_ray_setup(const __grid_constant_
         ry.tz = (float)((double)fr.T[2] / (double)vs);
         // fixed-point scale of the launch: every |w| and |w*ds| must fit 31 bits (|ds| <= max(L, n*vs - L) + vs)
         const float dmax = fmaxf(L, (float)n * vs - L) + vs;
-        fmax = fmaxf(ry.w, ry.w * dmax);
+        const unsigned fb = __float_as_uint(fminf(fmaxf(ry.w, ry.w * dmax), 3.0e38f));  // non-negative floats order like their bits
+        if (fb > my_fmax) my_fmax = fb;
         wide = n > 65535;
       }
     }
-    fmax = fminf(fmax, 3.0e38f);
-    {
-      unsigned fb = __float_as_uint(fmax);  // non-negative floats order like their bit patterns
-      fb = __reduce_max_sync(FULL, fb);
-      if ((threadIdx.x & 31) == 0 && fb > my_fmax) my_fmax = fb;
-    }
-    if (r < n_rays) {
-      float4* dst = reinterpret_cast<float4*>(&w.rays[r]);
-      dst[0] = make_float4(ry.ux, ry.uy, ry.uz, ry.L);
-      dst[1] = make_float4(ry.tx, ry.ty, ry.tz, ry.w);
-      w.aux[r] = ((uint32_t)min(n, 65535) << 16) | (f << 8) | (wide ? TS_AUX_WIDE : 0u);
-    }
-    if (wide && n > 65535) n = 65535;  // (never with sane configurations; keeps the aux word consistent)
-    walk_ray<false>(g, w, btab, live && n > 0, ry, r, n, s, wide, false, my_oob);
+    float4* dst = reinterpret_cast<float4*>(&w.rays[r]);
+    dst[0] = make_float4(ry.ux, ry.uy, ry.uz, ry.L);
+    dst[1] = make_float4(ry.tx, ry.ty, ry.tz, ry.w);
+    w.aux[r] = ((uint32_t)max(0, min(n, 65535)) << 16) | (f << 8) | (wide ? TS_AUX_WIDE : 0u);
   }
+  __shared__ unsigned int s_rays, s_fmax;
+  if (threadIdx.x == 0) { s_rays = 0u; s_fmax = 0u; }
+  __syncthreads();
   for (int o = 16; o > 0; o >>= 1) {
     my_rays += __shfl_xor_sync(FULL, my_rays, o);
-    my_oob += __shfl_xor_sync(FULL, my_oob, o);
+    my_fmax = max(my_fmax, __shfl_xor_sync(FULL, my_fmax, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    if (my_rays) atomicAdd(&ctr->n_rays, (unsigned long long)my_rays);
-    if (my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
-    if (my_fmax) atomicMax(&w.ctl->fmax_bits, my_fmax);
+    if (my_rays) atomicAdd(&s_rays, my_rays);
+    if (my_fmax) atomicMax(&s_fmax, my_fmax);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_rays) atomicAdd(&ctr->n_rays, (unsigned long long)s_rays);
+    if (s_fmax) atomicMax(&w.ctl->fmax_bits, s_fmax);
   }
 }
 
 // ---------------------------------------------------------------------------
-// K2b: scan of the per-block segment counts -> offsets + work items (one CTA)
+// K2b: segment walk: 3-D DDA over the 16^3 blocks in voxel-index space, one lane per ray, warp-uniform loop (one
+// block crossing per lane and iteration).  Segments are HINTS - every sample is re-checked exactly by the march
+// kernel - so the crossing parameters may be off by one step.
+// ---------------------------------------------------------------------------
+// 0 = far outside the volume (every sample is out of bounds), 1 = block inside the block range, 2 = outside but
+// adjacent to it (a rounding-boundary sample may still be in bounds: exact path)
+__device__ __forceinline__ int block_class(const TsGrid& g, int bx, int by, int bz) {
+  const int b0 = (-g.hN) >> TS_BSHIFT, b1 = (g.N - g.hN - 1) >> TS_BSHIFT;
+  const int z0 = (-g.hNz) >> TS_BSHIFT, z1 = (g.Nz - g.hNz - 1) >> TS_BSHIFT;
+  if (bx >= b0 && bx <= b1 && by >= b0 && by <= b1 && bz >= z0 && bz <= z1) return 1;
+  if (bx >= b0 - 1 && bx <= b1 + 1 && by >= b0 - 1 && by <= b1 + 1 && bz >= z0 - 1 && bz <= z1 + 1) return 2;
+  return 0;
+}
+__device__ __forceinline__ void gen_append(const TsMarchWs& w, int* err, uint32_t ray, int j, int cnt) {
+  const int p = atomicAdd(&w.ctl->n_gen, 1);
+  if ((uint32_t)p < w.gen_cap) w.gen[p] = TsSeg{ray, ((uint32_t)j << 12) | (uint32_t)cnt};
+  else atomicOr(err, TS_ERR_RAYLIST_FULL);
+}
+__device__ __forceinline__ void dda_axis(float u, float t, int& b, float& jc, float& dj, int& sg) {
+  b = __float2int_rn(u + t) >> TS_BSHIFT;  // block of the first sample (j = 1)
+  if (u > 0.0f) { jc = ((float)(16 * b + 16) - 0.5f - t) / u; dj = 16.0f / u; sg = 1; }
+  else if (u < 0.0f) { jc = ((float)(16 * b) - 0.5f - t) / u; dj = -16.0f / u; sg = -1; }
+  else { jc = 3.0e38f; dj = 0.0f; sg = 0; }
+}
+
+#define WK_CHUNK 4096   // entries per chunk of the per-CTA segment lists
+#define WK_MAXCH 1024   // chunks per CTA
+struct WalkSmem {
+  unsigned long long btab[RM_TAB];  // block coordinates -> pool index (direct mapped, rm_lookup)
+  uint32_t chunk[WK_MAXCH];         // first entry of the CTA's k-th chunk in tmp_seg / tmp_key
+  int n_chunk, cur, ovf, pad;
+};
+
+__global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
+                                                             const int* __restrict__ n_rays_f, uint32_t ray_cap_f, TsMarchWs w, TsCounters* ctr) {
+  extern __shared__ __align__(16) unsigned char ms_smem[];
+  WalkSmem& S = *reinterpret_cast<WalkSmem*>(ms_smem);
+  for (int e = threadIdx.x; e < RM_TAB; e += MS_THREADS) S.btab[e] = TS_EMPTY;
+  if (threadIdx.x == 0) { S.n_chunk = 0; S.cur = 0; S.ovf = 0; }
+  __syncthreads();
+  const uint32_t f = blockIdx.y;
+  const uint32_t nme = min((uint32_t)n_rays_f[f], ray_cap_f);
+  const int s = batch.f[f].submap;
+  const uint32_t lane = threadIdx.x & 31u;
+  const int max_seg_ray = (int)(in.max_steps * 0.125f) + 8;  // block crossings of the longest ray (+ slack)
+  unsigned int my_oob = 0;
+  for (uint32_t base = blockIdx.x * MS_THREADS; base < nme; base += gridDim.x * MS_THREADS) {
+    // room for this round's segments in the CTA's list
+    if (threadIdx.x == 0 && !S.ovf) {
+      const long long need = (long long)S.cur + (long long)MS_THREADS * max_seg_ray;
+      while ((long long)S.n_chunk * WK_CHUNK < need) {
+        uint32_t c0 = 0;
+        bool okc = S.n_chunk < WK_MAXCH;
+        if (okc) { c0 = atomicAdd(&w.ctl->tmp_cursor, (unsigned)WK_CHUNK); okc = c0 + WK_CHUNK <= w.seg_cap; }
+        if (!okc) { S.ovf = 1; break; }  // workspace exhausted: the rest of this CTA's rays take the generic path
+        S.chunk[S.n_chunk++] = c0;
+      }
+    }
+    __syncthreads();
+    const bool ovf = S.ovf != 0;
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t r = f * ray_cap_f + i;
+    float ux = 0.f, uy = 0.f, uz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    int n = 0;
+    bool wide = false;
+    if (i < nme) {
+      const float4* src = reinterpret_cast<const float4*>(&w.rays[r]);
+      const float4 a = src[0], b = src[1];
+      ux = a.x; uy = a.y; uz = a.z; tx = b.x; ty = b.y; tz = b.z;
+      const uint32_t ax = w.aux[r];
+      n = (int)(ax >> 16);
+      wide = (ax & TS_AUX_WIDE) != 0;
+    }
+    int bx, by, bz, sx, sy, sz;
+    float jx, jy, jz, dx, dy, dz;
+    dda_axis(ux, tx, bx, jx, dx, sx);
+    dda_axis(uy, ty, by, jy, dy, sy);
+    dda_axis(uz, tz, bz, jz, dz, sz);
+    // whole ray inside the block range (both end points are; the cells in between lie between them)?
+    bool inside = false;
+    if (n > 0) {
+      const float nf = (float)n;
+      const int ex = __float2int_rn(__fmaf_rn(ux, nf, tx)) >> TS_BSHIFT, ey = __float2int_rn(__fmaf_rn(uy, nf, ty)) >> TS_BSHIFT,
+                ez = __float2int_rn(__fmaf_rn(uz, nf, tz)) >> TS_BSHIFT;
+      inside = block_class(g, bx, by, bz) == 1 && block_class(g, ex, ey, ez) == 1;
+    }
+    const uint32_t rj = (f << 24);  // frame of the ray rides in the top byte of the segment word
+    int j = 1;
+    const int max_iter = 3 * (n / 16 + 4);
+    for (int it = 0;; ++it) {
+      const bool act = j <= n && it < max_iter;
+      if (!__any_sync(FULL, act)) break;
+      int cnt = 0, jl = 0;
+      if (act) {
+        const float je = fminf(fminf(jx, jy), jz);
+        jl = min((int)ceilf(je) - 1, n);  // last step strictly before the crossing
+        if (jl >= j) cnt = min(jl - j + 1, 32);
+      }
+      int key = -1;  // block * SEG_CLS + length class
+      if (cnt > 0) {
+        const int cls = inside ? 1 : block_class(g, bx, by, bz);
+        if (wide || cls == 2 || ovf) gen_append(w, g.err, r, j, cnt);
+        else if (cls == 0) my_oob += (unsigned)cnt;
+        else {
+          const int blk = rm_lookup(g, S.btab, ts_pack_key(s, bx, by, bz), bx, by, bz);  // activates + marks the block dirty
+          if (blk >= 0) key = blk * SEG_CLS + ((cnt - 1) >> 1);  // (< 0: pool exhausted, samples dropped)
+        }
+      }
+      const bool rec = key >= 0;
+      const unsigned mrec = __ballot_sync(FULL, rec);
+      if (mrec) {
+        const int leader = __ffs(mrec) - 1;
+        int p0 = 0;
+        if ((int)lane == leader) p0 = atomicAdd(&S.cur, __popc(mrec));
+        p0 = __shfl_sync(FULL, p0, leader);
+        if (rec) {
+          const int p = p0 + __popc(mrec & ((1u << lane) - 1u));
+          const uint32_t gp = S.chunk[p >> 12] + (uint32_t)(p & (WK_CHUNK - 1));
+          w.tmp_seg[gp] = TsSeg{r, rj | ((uint32_t)j << 8) | (uint32_t)cnt};
+          w.tmp_key[gp] = (uint32_t)key;
+          const unsigned grp = __match_any_sync(mrec, key);
+          if ((int)lane == __ffs(grp) - 1) red_add_u32((unsigned int*)&w.seg_count[key], (unsigned)__popc(grp));
+        }
+      }
+      j += cnt;
+      if (act && j > jl) {  // the run up to the crossing is out: step into the next block
+        if (jx <= jy && jx <= jz) { bx += sx; jx += dx; }
+        else if (jy <= jz) { by += sy; jy += dy; }
+        else { bz += sz; jz += dz; }
+      }
+    }
+    // non-finite pose: hand the rest to the exact path in bounded pieces
+    while (j <= n) { const int c = min(n - j + 1, 4095); gen_append(w, g.err, r, j, c); j += c; }
+  }
+  __syncthreads();
+  const uint32_t cta = blockIdx.y * gridDim.x + blockIdx.x;
+  uint32_t* cch = w.cta_chunk + (size_t)cta * WK_MAXCH;
+  for (int k = threadIdx.x; k < S.n_chunk; k += MS_THREADS) cch[k] = S.chunk[k];
+  if (threadIdx.x == 0) w.cta_n[cta] = S.cur;
+  for (int o = 16; o > 0; o >>= 1) my_oob += __shfl_xor_sync(FULL, my_oob, o);
+  if (lane == 0 && my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
+}
+
+// ---------------------------------------------------------------------------
+// K2c: per block with segments: class counts -> offsets inside the block's run (seg_rel), list of touched blocks.
+// seg_count is handed on zeroed: k_seg_place uses it as the fill cursor.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seg_class(TsGrid g, TsMarchWs w) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  const uint32_t lane = threadIdx.x & 31u;
+  const int stride = gridDim.x * 256;
+  for (int b0 = blockIdx.x * 256; b0 < nb; b0 += stride) {
+    const int b = b0 + (int)threadIdx.x;
+    unsigned tot = 0;
+    if (b < nb && g.dirty_flag[b]) {
+      uint4* c4 = reinterpret_cast<uint4*>(&w.seg_count[(size_t)b * SEG_CLS]);
+      uint4* r4 = reinterpret_cast<uint4*>(&w.seg_rel[(size_t)b * SEG_CLS]);
+#pragma unroll
+      for (int q = 0; q < SEG_CLS / 4; q++) {
+        const uint4 c = c4[q];
+        if ((c.x | c.y | c.z | c.w) == 0u) { continue; }
+        r4[q] = make_uint4(tot, tot + c.x, tot + c.x + c.y, tot + c.x + c.y + c.z);
+        tot += c.x + c.y + c.z + c.w;
+        c4[q] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    const unsigned mt = __ballot_sync(FULL, tot > 0u);
+    if (mt) {
+      const int leader = __ffs(mt) - 1;
+      int p0 = 0;
+      if ((int)lane == leader) p0 = atomicAdd(&w.ctl->n_touched, __popc(mt));
+      p0 = __shfl_sync(FULL, p0, leader);
+      if (tot > 0u) {
+        const int p = p0 + __popc(mt & ((1u << lane) - 1u));
+        w.touched[p] = b;
+        w.blk_total[p] = tot;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2d: scan over the touched blocks -> run offsets + work items (one CTA).  Full chunks go to the front of the item
+// list, the blocks' remainders to its back (taken last: the tail of the persistent march is made of small items).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_seg_scan(TsMarchWs w, TsCounters* ctr) {
-  __shared__ uint32_t s_a[32], s_b[32];
-  __shared__ uint32_t s_run[2];
+  __shared__ uint32_t s_a[32], s_b[32], s_c[32];
+  __shared__ uint32_t s_run[3];
   const int nt = w.ctl->n_touched;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { s_run[0] = 0; s_run[1] = 0; }
+  if (threadIdx.x == 0) { s_run[0] = 0; s_run[1] = 0; s_run[2] = 0; }
   __syncthreads();
   for (int base = 0; base < nt; base += 1024) {
     const int i = base + threadIdx.x;
     int blk = -1;
     uint32_t cnt = 0;
-    if (i < nt) { blk = w.touched[i]; cnt = (uint32_t)w.seg_count[blk]; }
-    const uint32_t items = (cnt + MR_CHUNK - 1) / MR_CHUNK;
-    uint32_t a = cnt, b = items;  // inclusive warp scans
+    if (i < nt) { blk = w.touched[i]; cnt = w.blk_total[i]; }
+    const uint32_t full = cnt / MR_CHUNK, part = (cnt % MR_CHUNK) ? 1u : 0u;
+    uint32_t a = cnt, b = full, c = part;  // inclusive warp scans
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o);
-      if (lane >= o) { a += ta; b += tb; }
+      const uint32_t ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o), tc = __shfl_up_sync(FULL, c, o);
+      if (lane >= o) { a += ta; b += tb; c += tc; }
     }
-    if (lane == 31) { s_a[wid] = a; s_b[wid] = b; }
+    if (lane == 31) { s_a[wid] = a; s_b[wid] = b; s_c[wid] = c; }
     __syncthreads();
     if (wid == 0) {
-      uint32_t ta = s_a[lane], tb = s_b[lane];
+      uint32_t ta = s_a[lane], tb = s_b[lane], tc = s_c[lane];
       for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t ua = __shfl_up_sync(FULL, ta, o), ub = __shfl_up_sync(FULL, tb, o);
-        if (lane >= o) { ta += ua; tb += ub; }
+        const uint32_t ua = __shfl_up_sync(FULL, ta, o), ub = __shfl_up_sync(FULL, tb, o), uc = __shfl_up_sync(FULL, tc, o);
+        if (lane >= o) { ta += ua; tb += ub; tc += uc; }
       }
-      s_a[lane] = ta; s_b[lane] = tb;  // inclusive over warps
+      s_a[lane] = ta; s_b[lane] = tb; s_c[lane] = tc;  // inclusive over warps
     }
     __syncthreads();
-    const uint32_t run_seg = s_run[0], run_item = s_run[1];
-    const uint32_t ex_seg = run_seg + (wid ? s_a[wid - 1] : 0u) + a - cnt;
-    const uint32_t ex_item = run_item + (wid ? s_b[wid - 1] : 0u) + b - items;
+    const uint32_t ex_seg = s_run[0] + (wid ? s_a[wid - 1] : 0u) + a - cnt;
+    const uint32_t ex_full = s_run[1] + (wid ? s_b[wid - 1] : 0u) + b - full;
+    const uint32_t ex_part = s_run[2] + (wid ? s_c[wid - 1] : 0u) + c - part;
     if (i < nt) {
       w.seg_off[blk] = ex_seg;
-      w.seg_count[blk] = 0;  // becomes the fill cursor
-      for (uint32_t q = 0; q < items; q++) {
-        const uint32_t p = ex_item + q;
-        if (p < w.item_cap) w.items[p] = TsItem{blk, ex_seg + q * MR_CHUNK, min((uint32_t)MR_CHUNK, cnt - q * MR_CHUNK), 0u};
-      }
+      for (uint32_t q = 0; q < full; q++)
+        if (ex_full + q < w.item_cap) w.items[ex_full + q] = TsItem{blk, ex_seg + q * MR_CHUNK, (uint32_t)MR_CHUNK, 0u};
+      if (part && ex_part < w.item_cap) w.items[w.item_cap - 1 - ex_part] = TsItem{blk, ex_seg + full * MR_CHUNK, cnt - full * MR_CHUNK, 0u};
     }
     __syncthreads();
-    if (threadIdx.x == 0) { s_run[0] = run_seg + s_a[31]; s_run[1] = run_item + s_b[31]; }
+    if (threadIdx.x == 0) { s_run[0] += s_a[31]; s_run[1] += s_b[31]; s_run[2] += s_c[31]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const uint32_t tot = s_run[0], ni = s_run[1];
-    const bool ovf = tot > w.seg_cap || ni > w.item_cap;
+    const uint32_t tot = s_run[0], nfull = s_run[1], npart = s_run[2];
+    const bool ovf = nfull + npart > w.item_cap;  // (segments cannot exceed seg_cap: they come out of the same pool)
     w.ctl->total_segs = tot;
     w.ctl->overflow = ovf ? 1 : 0;
-    w.ctl->n_items = ovf ? 0 : (int)ni;
+    w.ctl->n_full = ovf ? 0 : (int)nfull;
+    w.ctl->n_items = ovf ? 0 : (int)(nfull + npart);
     // fixed-point scale: the largest k with fmax * 2^k < 2^30, clamped to [0, 48]
     const float fm = __uint_as_float(w.ctl->fmax_bits);
     int k = 30;
@@ -306,46 +376,60 @@ __global__ void __launch_bounds__(1024) k_seg_scan(TsMarchWs w, TsCounters* ctr)
     }
     w.ctl->scale_k = max(0, min(48, k));
     atomicAdd(&ctr->n_segs, (unsigned long long)tot);
-    atomicAdd(&ctr->n_items, (unsigned long long)(ovf ? 0u : ni));
+    atomicAdd(&ctr->n_items, (unsigned long long)(ovf ? 0u : nfull + npart));
   }
 }
 
 // ---------------------------------------------------------------------------
-// K2c: segment fill
+// K2e: placement.  Same grid as k_seg_walk: CTA i moves the segments of its list into the blocks' runs:
+// seg_off[block] + seg_rel[block, class] + cursor (warp-aggregated global atomic on seg_count, zero on entry).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(MS_THREADS) k_seg_fill(const __grid_constant__ TsBatch batch, TsGrid g, const int* __restrict__ n_rays_p,
-                                                          uint32_t ray_cap, TsMarchWs w) {
-  __shared__ unsigned long long btab[RM_TAB];
-  for (int e = threadIdx.x; e < RM_TAB; e += MS_THREADS) btab[e] = TS_EMPTY;
+__global__ void __launch_bounds__(MS_THREADS) k_seg_place(TsMarchWs w) {
+  __shared__ uint32_t s_chunk[WK_MAXCH];
+  const uint32_t cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int total = w.cta_n[cta];
+  if (total == 0) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t* cch = w.cta_chunk + (size_t)cta * WK_MAXCH;
+  const int nch = (total + WK_CHUNK - 1) / WK_CHUNK;
+  for (int k = threadIdx.x; k < nch; k += MS_THREADS) s_chunk[k] = cch[k];
   __syncthreads();
-  const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
-  const bool overflow = w.ctl->overflow != 0;
-  unsigned int dummy = 0;
-  for (uint32_t base = blockIdx.x * MS_THREADS; base < n_rays; base += gridDim.x * MS_THREADS) {
-    const uint32_t r = base + threadIdx.x;
-    TsRay ry;
-    ry.ux = ry.uy = ry.uz = ry.L = ry.tx = ry.ty = ry.tz = ry.w = 0.0f;
-    int n = 0, s = 0;
-    bool wide = false;
-    if (r < n_rays) {
-      const float4* src = reinterpret_cast<const float4*>(&w.rays[r]);
-      const float4 a = src[0], b = src[1];
-      ry.ux = a.x; ry.uy = a.y; ry.uz = a.z; ry.L = a.w; ry.tx = b.x; ry.ty = b.y; ry.tz = b.z; ry.w = b.w;
-      const uint32_t ax = w.aux[r];
-      n = (int)(ax >> 16);
-      s = batch.f[(ax >> 8) & 255u].submap;
-      wide = (ax & TS_AUX_WIDE) != 0;
+  const bool overflow = w.ctl->overflow != 0;  // work list did not fit: every segment goes to the generic path
+  for (int p0 = (threadIdx.x & ~31); p0 < total; p0 += MS_THREADS) {
+    const int p = p0 + (int)lane;
+    const bool have = p < total;
+    TsSeg sg = TsSeg{0u, 0u};
+    int key = -1;
+    if (have) {
+      const uint32_t gp = s_chunk[p >> 12] + (uint32_t)(p & (WK_CHUNK - 1));
+      sg = w.tmp_seg[gp];
+      key = (int)w.tmp_key[gp];
     }
-    walk_ray<true>(g, w, btab, n > 0, ry, r, n, s, wide, overflow, dummy);
+    if (overflow) {
+      if (have) {
+        const int pg = atomicAdd(&w.ctl->n_gen, 1);
+        if ((uint32_t)pg < w.gen_cap) w.gen[pg] = TsSeg{sg.ray, (((sg.jc >> 8) & 0xFFFFu) << 12) | (sg.jc & 255u)};
+      }
+      continue;
+    }
+    const unsigned mh = __ballot_sync(FULL, have);
+    if (have) {
+      const unsigned grp = __match_any_sync(mh, key);
+      const int leader = __ffs(grp) - 1;
+      int c0 = 0;
+      if ((int)lane == leader) c0 = atomicAdd(&w.seg_count[key], __popc(grp));
+      c0 = __shfl_sync(grp, c0, leader) + __popc(grp & ((1u << lane) - 1u));
+      w.seg[w.seg_off[key / SEG_CLS] + w.seg_rel[key] + (uint32_t)c0] = sg;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
 // exact sample index, as the reference states it (:253-254)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void exact_index(const TsRay& ry, const float* T, int j, float vs, float rvs, int& xi, int& yi, int& zi) {
+__device__ __forceinline__ void exact_index(float ux, float uy, float uz, const float* T, int j, float vs, float rvs, int& xi, int& yi, int& zi) {
   const float jf = (float)j;
-  const float x = (ry.ux * jf) * vs + T[0], y = (ry.uy * jf) * vs + T[1], z = (ry.uz * jf) * vs + T[2];
+  const float x = (ux * jf) * vs + T[0], y = (uy * jf) * vs + T[1], z = (uz * jf) * vs + T[2];
   xi = iroundf(div_vs(x, vs, rvs));
   yi = iroundf(div_vs(y, vs, rvs));
   zi = iroundf(div_vs(z, vs, rvs));
@@ -367,8 +451,25 @@ __device__ __forceinline__ void global_sample(const TsGrid& g, int s, int xi, in
 }
 
 // ---------------------------------------------------------------------------
-// K2d: the march proper.  Persistent CTAs, one work item (block, <= MR_CHUNK segments) at a time.
+// K2f: the march proper.  Persistent CTAs, one work item (block, <= MR_CHUNK segments) at a time.
+//
+// A block's run is ordered by segment length (k_seg_place), so the 32 segments a warp takes - ONE PER LANE, ray
+// parameters in registers - have (nearly) equal length and are walked in lock step.  Lane l starts at step
+// (7*l mod cnt) of its segment and wraps around: neighbouring rays are nearly parallel, so with every lane at a
+// different depth the 32 shared-memory atomics of a step hit 32 different voxels (same-step marching puts 4-16 rays
+// into one voxel half way to the surface: serialised atomics).
+//
+// Shared accumulators per voxel: two 64-bit sums (A = sum w*ds, B = sum w, units 2^-scale_k) kept as
+//   lo  = sum x      mod 2^32
+//   hi' = sum (x >> 16)            (arithmetic shift)
+// Both are plain no-return ATOMS.ADD - no carry logic, no dependent read of the old value.  With fewer than 2^16
+// samples per voxel and item (MR_CHUNK segments x <= 2 samples of a ray in one voxel) the true sum S is the unique
+// value with S = lo (mod 2^32) in [hi' * 2^16, hi' * 2^16 + 2^32):  S = hi' * 2^16 + ((lo - (hi' << 16)) mod 2^32).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ double mb_sum(unsigned int lo, int hi) {
+  return (double)((long long)hi * 65536ll + (long long)(unsigned int)(lo - ((unsigned int)hi << 16)));
+}
+
 template <bool VERIFY>
 __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsMarchWs w,
                                                                  TsCounters* ctr) {
@@ -377,7 +478,6 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
   int* const a_hi = (int*)(mb_smem + MB_WORDS);
   unsigned int* const b_lo = mb_smem + 2 * MB_WORDS;
   int* const b_hi = (int*)(mb_smem + 3 * MB_WORDS);
-  MbWarp* const ws = reinterpret_cast<MbWarp*>(mb_smem + 4 * MB_WORDS) + (threadIdx.x >> 5);
   __shared__ int s_item;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const float vs = in.vs, rvs = in.rvs, eps_hi = 0.5f - w.near_eps;
@@ -386,87 +486,87 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
   const double unfix = 1.0 / (double)fix;
   unsigned int my_upd = 0, my_oob = 0, my_slow = 0, my_fb = 0, my_bad = 0;
   for (int e = threadIdx.x; e < 4 * MB_WORDS; e += MB_THREADS) mb_smem[e] = 0u;
-  const int n_items = w.ctl->n_items;
+  const int n_items = w.ctl->n_items, n_full = w.ctl->n_full;
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) s_item = atomicAdd(&w.ctl->item_cursor, 1);
     __syncthreads();
     const int it = s_item;
     if (it >= n_items) break;
-    const TsItem item = w.items[it];
+    const TsItem item = w.items[it < n_full ? it : (int)w.item_cap - 1 - (it - n_full)];
     int sm, kx, ky, kz;
     ts_unpack_key(g.block_key[item.blk], sm, kx, ky, kz);
     const int ox = kx << TS_BSHIFT, oy = ky << TS_BSHIFT, oz = kz << TS_BSHIFT;
     const float fox = (float)ox, foy = (float)oy, foz = (float)oz;
     // blocks cut by the volume boundary (N not a multiple of 16) need the per-sample bounds test
     const bool partial = ox < -g.hN || ox + TS_B > g.N - g.hN || oy < -g.hN || oy + TS_B > g.N - g.hN || oz < -g.hNz || oz + TS_B > g.Nz - g.hNz;
-    for (uint32_t sb = wid * 32u; sb < item.nseg; sb += MB_WARPS * 32u) {
-      // ---- stage 32 segments: ray records in block-local coordinates, flattened sample map ----
-      int cnt = 0;
-      uint32_t rid = 0;
-      int j0 = 0;
-      if (sb + lane < item.nseg) {
-        const TsSeg sg = w.seg[item.seg0 + sb + lane];
-        rid = sg.ray; j0 = (int)(sg.jc >> 8); cnt = (int)(sg.jc & 255u);
+    const int nseg = (int)item.nseg;
+    const TsSeg* const segs = w.seg + item.seg0;
+    // ---- 32 segments per warp, one per lane; the next batch's records are fetched while this one is marched ----
+    TsSeg nx = TsSeg{0u, 0u};
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+    {
+      const int i0 = (int)wid * 32 + (int)lane;
+      if (i0 < nseg) {
+        nx = segs[i0];
+        const float4* src = reinterpret_cast<const float4*>(&w.rays[nx.ray]);
+        na = __ldg(src); nb = __ldg(src + 1);
       }
-      int incl = cnt;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, o);
-        if ((int)lane >= o) incl += t;
+    }
+    for (int sb = (int)wid * 32; sb < nseg; sb += MB_WARPS * 32) {
+      const TsSeg sg = nx;
+      const float4 a = na, b = nb;
+      {
+        const int i1 = sb + MB_WARPS * 32 + (int)lane;
+        nx = TsSeg{0u, 0u};
+        if (i1 < nseg) {
+          nx = segs[i1];
+          const float4* src = reinterpret_cast<const float4*>(&w.rays[nx.ray]);
+          na = __ldg(src); nb = __ldg(src + 1);
+        }
       }
-      const int total = __shfl_sync(FULL, incl, 31);
-      const int excl = incl - cnt;
-      if (cnt > 0) {
-        const float4* src = reinterpret_cast<const float4*>(&w.rays[rid]);
-        const float4 a = __ldg(src), b = __ldg(src + 1);
-        const float jf = (float)j0;
-        // first sample of the segment in block-local voxel units: one rounding at magnitude <= ~20
-        const float x0 = __fmaf_rn(a.x, jf, b.x - fox), y0 = __fmaf_rn(a.y, jf, b.y - foy), z0 = __fmaf_rn(a.z, jf, b.z - foz);
-        ws->ra[lane] = make_float4(a.x, a.y, a.z, x0);
-        ws->rb[lane] = make_float4(y0, z0, __fmaf_rn(-jf, vs, a.w), b.w);
-        ws->j0[lane] = j0;
-        ws->rid[lane] = rid;
-        for (int q = 0; q < cnt; q++) ws->map[excl + q] = (unsigned short)((lane << 8) | (unsigned)q);
-      }
-      __syncwarp();
-      // ---- the samples, flattened over the lanes ----
-      for (int sidx = (int)lane; sidx - (int)lane < total; sidx += 32) {
-        const bool have = sidx < total;
-        const unsigned m = have ? ws->map[sidx] : 0u;
-        const unsigned sl = m >> 8;
-        const float kf = (float)(m & 255u);
-        const float4 A = ws->ra[sl], B = ws->rb[sl];
-        const float gx = __fmaf_rn(A.x, kf, A.w), gy = __fmaf_rn(A.y, kf, B.x), gz = __fmaf_rn(A.z, kf, B.y);
+      const int cnt = (int)(sg.jc & 255u);  // 0 for lanes past the end of the item
+      const int j0 = (int)((sg.jc >> 8) & 0xFFFFu);
+      const uint32_t frame = sg.jc >> 24;
+      const int maxc = __reduce_max_sync(FULL, cnt);
+      const float jf = (float)j0;
+      const float ux = a.x, uy = a.y, uz = a.z;
+      // first sample of the segment in block-local voxel units: one rounding at magnitude <= ~20
+      const float x0 = __fmaf_rn(a.x, jf, b.x - fox), y0 = __fmaf_rn(a.y, jf, b.y - foy), z0 = __fmaf_rn(a.z, jf, b.z - foz);
+      const float L0 = __fmaf_rn(-jf, vs, a.w);
+      const float wf = b.w * fix;  // w in fixed-point units (exact: power of two)
+      const int wq = __float2int_rn(wf);
+      const bool tiny = wq < MB_MIN_WQ;  // weight far below the launch's largest: f32 reductions keep its relative precision
+      const float cntf = (float)cnt;
+      float kf = 0.0f;
+      if (cnt > 1) kf = (float)((int)(lane * 7u) % cnt);  // staggered start
+      auto sample = [&](const bool pred, auto PARTIAL) __attribute__((always_inline)) {
+        const float gx = __fmaf_rn(ux, kf, x0), gy = __fmaf_rn(uy, kf, y0), gz = __fmaf_rn(uz, kf, z0);
         // round to nearest + distance of the fraction from .5 (magic-number rounding: |g| < 2^22)
         const float tx = gx + 12582912.0f, ty = gy + 12582912.0f, tz = gz + 12582912.0f;
         int lx = __float_as_int(tx) - 0x4B400000, ly = __float_as_int(ty) - 0x4B400000, lz = __float_as_int(tz) - 0x4B400000;
         const float rx = gx - (tx - 12582912.0f), ry = gy - (ty - 12582912.0f), rz = gz - (tz - 12582912.0f);
-        const bool near = fabsf(rx) > eps_hi || fabsf(ry) > eps_hi || fabsf(rz) > eps_hi;
-        bool ok = have;
-        bool slow = have && (near || (((unsigned)(lx | ly | lz)) > 15u) || VERIFY);
-        const float ds = __fmaf_rn(-kf, vs, B.z);  // L - j*vs
-        const float av = B.w * ds;                  // w * ds (:264)
+        const bool near = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) > eps_hi;
+        bool ok = pred;
+        const bool slow = pred && (near || (((unsigned)(lx | ly | lz)) > 15u) || tiny || VERIFY);
+        const float ds = __fmaf_rn(-kf, vs, L0);  // L - j*vs
+        const float avq = wf * ds;                 // w * ds (:264) in fixed-point units
         if (__any_sync(FULL, slow)) {
           if (slow) {  // exact index (:253-254); a sample that really lies in another block goes through the global path
-            const uint32_t rid2 = ws->rid[sl];
-            const int j = ws->j0[sl] + (int)(m & 255u);
-            TsRay ryx;
-            ryx.ux = A.x; ryx.uy = A.y; ryx.uz = A.z;
-            const TsFrame& fr = batch.f[(w.aux[rid2] >> 8) & 255u];
             int xi, yi, zi;
-            exact_index(ryx, fr.T, j, vs, rvs, xi, yi, zi);
+            exact_index(ux, uy, uz, batch.f[frame].T, j0 + (int)kf, vs, rvs, xi, yi, zi);
             const int ex = xi - ox, ey = yi - oy, ez = zi - oz;
             if (VERIFY && !near && (ex != lx || ey != ly || ez != lz)) my_bad++;
             if (near) my_slow++;
             lx = ex; ly = ey; lz = ez;
-            if (((unsigned)(lx | ly | lz)) > 15u) {
+            if (tiny || ((unsigned)(lx | ly | lz)) > 15u) {
               ok = false;
               my_fb++;
-              global_sample(g, sm, xi, yi, zi, av, B.w, my_upd, my_oob);
+              global_sample(g, sm, xi, yi, zi, (float)((double)avq * unfix), (float)((double)wf * unfix), my_upd, my_oob);
             }
           }
         }
-        if (ok && partial) {
+        if (decltype(PARTIAL)::value && ok) {
           const int xi = lx + ox, yi = ly + oy, zi = lz + oz;
           if (!((unsigned)(xi + g.hN) < (unsigned)g.N && (unsigned)(yi + g.hN) < (unsigned)g.N && (unsigned)(zi + g.hNz) < (unsigned)g.Nz)) {
             ok = false;
@@ -474,19 +574,22 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
           }
         }
         if (ok) {
-          const int wq = __float2int_rn(B.w * fix);
-          if (wq >= MB_MIN_WQ) {
-            const int e = lx * MB_SX + ly * MB_SY + lz;
-            lohi_add(&a_lo[e], &a_hi[e], __float2int_rn(av * fix));
-            lohi_add(&b_lo[e], &b_hi[e], wq);
-            my_upd++;
-          } else {  // weight far below the launch's largest: f32 reduction keeps its relative precision
-            my_fb++;
-            global_sample(g, sm, lx + ox, ly + oy, lz + oz, av, B.w, my_upd, my_oob);
-          }
+          const int e = lx * MB_SX + ly * MB_SY + lz;
+          const int xq = __float2int_rn(avq);
+          atomicAdd(&a_lo[e], (unsigned int)xq);
+          atomicAdd(&a_hi[e], xq >> 16);
+          atomicAdd(&b_lo[e], (unsigned int)wq);
+          atomicAdd(&b_hi[e], wq >> 16);
+          my_upd++;
         }
+        kf += 1.0f;
+        if (kf >= cntf) kf = 0.0f;
+      };
+      if (partial) {
+        for (int i = 0; i < maxc; ++i) sample(i < cnt, std::true_type{});
+      } else {
+        for (int i = 0; i < maxc; ++i) sample(i < cnt, std::false_type{});
       }
-      __syncwarp();
     }
     __syncthreads();
     // ---- flush: one coalesced reduction per touched voxel, accumulators back to zero ----
@@ -499,9 +602,7 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
       const unsigned int alo = a_lo[e];
       const int ahi = a_hi[e];
       a_lo[e] = 0u; a_hi[e] = 0; b_lo[e] = 0u; b_hi[e] = 0;
-      const float Av = (float)(((double)ahi * 4294967296.0 + (double)alo) * unfix);
-      const float Bv = (float)(((double)bhi * 4294967296.0 + (double)blo) * unfix);
-      red_add_f32x2(&acc[v], Av, Bv);
+      red_add_f32x2(&acc[v], (float)(mb_sum(alo, ahi) * unfix), (float)(mb_sum(blo, bhi) * unfix));
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -521,7 +622,7 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
 }
 
 // ---------------------------------------------------------------------------
-// K2e: generic path - exact index and one global reduction per sample
+// K2g: generic path - exact index and one global reduction per sample
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_march_generic(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsMarchWs w, TsCounters* ctr) {
   const int n_gen = min(w.ctl->n_gen, (int)w.gen_cap);
@@ -530,16 +631,14 @@ __global__ void __launch_bounds__(256) k_march_generic(const __grid_constant__ T
     const TsSeg sg = w.gen[i];
     const float4* src = reinterpret_cast<const float4*>(&w.rays[sg.ray]);
     const float4 a = src[0], b = src[1];
-    TsRay ry;
-    ry.ux = a.x; ry.uy = a.y; ry.uz = a.z; ry.L = a.w; ry.w = b.w;
     const TsFrame& fr = batch.f[(w.aux[sg.ray] >> 8) & 255u];
     const int j0 = (int)(sg.jc >> 12), cnt = (int)(sg.jc & 4095u);
     for (int q = 0; q < cnt; q++) {
       const int j = j0 + q;
       int xi, yi, zi;
-      exact_index(ry, fr.T, j, in.vs, in.rvs, xi, yi, zi);
-      const float ds = __fmaf_rn(-(float)j, in.vs, ry.L);
-      global_sample(g, fr.submap, xi, yi, zi, ry.w * ds, ry.w, my_upd, my_oob);
+      exact_index(a.x, a.y, a.z, fr.T, j, in.vs, in.rvs, xi, yi, zi);
+      const float ds = __fmaf_rn(-(float)j, in.vs, a.w);
+      global_sample(g, fr.submap, xi, yi, zi, b.w * ds, b.w, my_upd, my_oob);
       my_gen++;
     }
   }
@@ -555,11 +654,11 @@ __global__ void __launch_bounds__(256) k_march_generic(const __grid_constant__ T
   }
 }
 
-// end of a launch: per-block counters back to zero, control block cleared
+// end of a launch: fill cursors back to zero, control block cleared
 __global__ void __launch_bounds__(256) k_march_reset(TsMarchWs w) {
   const int nt = w.ctl->n_touched;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int q = i; q < nt; q += gridDim.x * blockDim.x) w.seg_count[w.touched[q]] = 0;
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < nt * (SEG_CLS / 4); q += gridDim.x * 256)
+    reinterpret_cast<uint4*>(w.seg_count + (size_t)w.touched[q / (SEG_CLS / 4)] * SEG_CLS)[q % (SEG_CLS / 4)] = make_uint4(0u, 0u, 0u, 0u);
   // the last CTA to finish clears the control block
   __shared__ int s_last;
   __syncthreads();
@@ -580,21 +679,31 @@ int ts_march_alloc(tslam_tsdf* m) {
   const size_t nb = (size_t)m->g.max_blocks;
   TS_CUDA(cudaMalloc(&w.rays, nr * sizeof(TsRay)));
   TS_CUDA(cudaMalloc(&w.aux, nr * 4));
-  size_t sc = nr * 4;
+  size_t sc = nr * 16;  // ~8 segments per 90-step ray on the bench stream, 15 on 8 m rays
   if (sc < (8u << 20)) sc = 8u << 20;
-  if (sc > (64u << 20)) sc = 64u << 20;
+  if (sc > (128u << 20)) sc = 128u << 20;
   const char* e = getenv("TSLAM_SEG_CAP");  // tests: force the overflow path
   if (e && atoll(e) > 0) sc = (size_t)atoll(e);
   w.seg_cap = (uint32_t)sc;
   TS_CUDA(cudaMalloc(&w.seg, sc * sizeof(TsSeg)));
-  TS_CUDA(cudaMalloc(&w.seg_count, nb * 4));
-  TS_CUDA(cudaMemset(w.seg_count, 0, nb * 4));
+  TS_CUDA(cudaMalloc(&w.tmp_seg, sc * sizeof(TsSeg)));
+  TS_CUDA(cudaMalloc(&w.tmp_key, sc * 4));
+  TS_CUDA(cudaMalloc(&w.seg_count, nb * SEG_CLS * 4));
+  TS_CUDA(cudaMemset(w.seg_count, 0, nb * SEG_CLS * 4));
+  TS_CUDA(cudaMalloc(&w.seg_rel, nb * SEG_CLS * 4));
   TS_CUDA(cudaMalloc(&w.seg_off, nb * 4));
   TS_CUDA(cudaMalloc(&w.touched, nb * 4));
+  TS_CUDA(cudaMalloc(&w.blk_total, nb * 4));
   w.item_cap = (uint32_t)(sc / MR_CHUNK + nb + 16);
   TS_CUDA(cudaMalloc(&w.items, (size_t)w.item_cap * sizeof(TsItem)));
   w.gen_cap = (uint32_t)(nr > (1u << 20) ? nr : (1u << 20));
   TS_CUDA(cudaMalloc(&w.gen, (size_t)w.gen_cap * sizeof(TsSeg)));
+  w.walk_x_max = m->sm_count * 3;
+  const size_t ncta = (size_t)w.walk_x_max + TSLAM_MAX_BATCH + 8;  // gx * nf <= 3 * SMs + nf
+  TS_CUDA(cudaMalloc(&w.cta_n, ncta * 4));
+  TS_CUDA(cudaMemset(w.cta_n, 0, ncta * 4));
+  TS_CUDA(cudaMalloc(&w.cta_chunk, ncta * WK_MAXCH * 4));
+  TS_CUDA(cudaFuncSetAttribute(k_seg_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
   TS_CUDA(cudaMalloc(&w.ctl, sizeof(TsMarchCtl)));
   TS_CUDA(cudaMemset(w.ctl, 0, sizeof(TsMarchCtl)));
   // |fast index - exact index| bound in voxel units (DESIGN.md "exact indices from a one-FMA fast path"):
@@ -615,20 +724,28 @@ int ts_march_alloc(tslam_tsdf* m) {
 
 void ts_march_free(tslam_tsdf* m) {
   TsMarchWs& w = m->mw;
-  cudaFree(w.rays); cudaFree(w.aux); cudaFree(w.seg); cudaFree(w.seg_count); cudaFree(w.seg_off); cudaFree(w.touched);
-  cudaFree(w.items); cudaFree(w.gen); cudaFree(w.ctl);
+  cudaFree(w.rays); cudaFree(w.aux); cudaFree(w.seg); cudaFree(w.tmp_seg); cudaFree(w.tmp_key); cudaFree(w.seg_count); cudaFree(w.seg_rel);
+  cudaFree(w.seg_off); cudaFree(w.touched); cudaFree(w.blk_total); cudaFree(w.items); cudaFree(w.gen); cudaFree(w.ctl); cudaFree(w.cta_n);
+  cudaFree(w.cta_chunk);
 }
 
-// sub_ev (profiling, may be null): 4 events recorded after set-up, scan, fill and the march kernels
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, cudaEvent_t* sub_ev) {
+// nf = frames of the launch (their rays sit in bdata[f * ray_cap_f ...]).
+// sub_ev (profiling, may be null): 4 events recorded after ray set-up, walk + class + scan, placement and the march kernels
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* sub_ev) {
   const int sms = m->sm_count;
-  k_ray_setup<<<sms * 4, MS_THREADS, 0, st>>>(batch, m->in, m->g, m->buckets, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters);
+  const int gx = nf > 1 ? (sms * 3 + nf - 1) / nf : m->mw.walk_x_max;  // CTAs per frame: ~3 per SM over the launch
+  const uint32_t cap_f = nf > 1 ? m->ray_cap_f : m->ray_list_cap;       // (a point cloud is one frame of up to max_points rays)
+  k_ray_setup<<<dim3(gx * 2, nf), 256, 0, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->n_rays_f, cap_f, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[0], st));
+  k_seg_walk<<<dim3(gx, nf), MS_THREADS, (int)sizeof(WalkSmem), st>>>(batch, m->in, m->g, m->n_rays_f, cap_f, m->mw, m->counters);
+  TS_LAUNCH_CHECK(m);
+  k_seg_class<<<sms * 2, 256, 0, st>>>(m->g, m->mw);
+  TS_LAUNCH_CHECK(m);
   k_seg_scan<<<1, 1024, 0, st>>>(m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[1], st));
-  k_seg_fill<<<sms * 4, MS_THREADS, 0, st>>>(batch, m->g, m->n_rays, m->ray_list_cap, m->mw);
+  k_seg_place<<<dim3(gx, nf), MS_THREADS, 0, st>>>(m->mw);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[2], st));
   const int grid = (sms - m->rm_reserve) * 2;

@@ -44,97 +44,117 @@ __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz)
            (unsigned long long)(bz + (1 << 20))) + 1ull);
 }
 
-__device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+// accumulate one unprojected point per lane into the frame's buckets.  process_point (dense_tsdf.py:227-234) with
+// exact fixed-point sums.  Two levels (round 2): a table of 16-byte SLOTS (key -> ray index) found by hashing, and
+// the DENSE per-ray array `bdata` that holds the sums.  A ray index is handed out when a bucket is opened, in open
+// order - the rays of a pixel tile are neighbours in `bdata`, so the reductions of a frame hit a compact,
+// L2-resident range and every later pass reads the rays sequentially (round 1 kept the sums inside a 64-byte hash
+// entry: 537 MB of tables, every access a random DRAM sector - ncu: k_ray_setup 157 us at 20 G sectors/s).
+// Lanes of a warp that fall into the same bucket (neighbouring pixels usually do) are merged first (match.any +
+// redux): one probe and one set of reductions per distinct bucket per warp instead of per pixel.
+// Must be called by all 32 lanes; `valid` masks lanes without a point.
+__device__ __forceinline__ uint32_t slot_hash(int bx, int by, int bz) {
+  // locality-preserving: a 4x4x2 group of buckets shares one 512-byte run of slots (a surface patch fills ~1/3 of
+  // it), groups are scattered by a multiplicative hash
+  uint32_t g = ((uint32_t)(bx >> 2) * 0x9E3779B1u) ^ ((uint32_t)(by >> 2) * 0x85EBCA77u) ^ ((uint32_t)(bz >> 1) * 0xC2B2AE3Du);
+  g ^= g >> 15;
+  return (g << 5) | (uint32_t)((bx & 3) | ((by & 3) << 2) | ((bz & 1) << 4));
 }
-__device__ __forceinline__ void red_add_u32(unsigned int* addr, unsigned int v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
-}
-
-// accumulate one unprojected point per lane into the frame's bucket table.
-// process_point (dense_tsdf.py:227-234) with exact fixed-point sums.  Lanes of a warp that fall into
-// the same bucket (neighbouring pixels usually do) are merged first (match.any + redux): one probe and
-// one set of reductions per distinct bucket per warp instead of per pixel.  Must be called by all 32
-// lanes; `valid` masks lanes without a point.  Returns the table slot when this lane OPENED a bucket
-// (the bucket becomes one ray; the caller appends it to the ray list), else -1.
-__device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, float px, float py, float pz, float dep,
-                                                 float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
+__device__ __forceinline__ void bucket_accumulate(bool valid, TsSlot* tab, uint32_t tab_base, uint32_t cap_mask, TsBucket* bdata, uint32_t ray_base,
+                                                  uint32_t ray_cap_f, int* n_rays_f, uint32_t frame, float px, float py, float pz, float dep,
+                                                  float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return -1;
-  const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
-  const unsigned long long key = bucket_key(bx, by, bz);
-  long long qx = __float2ll_rn(px * FIXQ), qy = __float2ll_rn(py * FIXQ), qz = __float2ll_rn(pz * FIXQ), qd = __float2ll_rn(dep * FIXQ);
-  int cnt = 1;
-  if (agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
-    const unsigned grp = __match_any_sync(vmask, key);
-    const bool leader = (threadIdx.x & 31) == (__ffs(grp) - 1);
-    cnt = __popc(grp);
-    if (cnt > 1) {
-      qx = (long long)__reduce_add_sync(grp, (int)qx);
-      qy = (long long)__reduce_add_sync(grp, (int)qy);
-      qz = (long long)__reduce_add_sync(grp, (int)qz);
-      qd = (long long)__reduce_add_sync(grp, (int)qd);
-      if (tex) {
-        cr = __reduce_add_sync(grp, cr);
-        cg = __reduce_add_sync(grp, cg);
-        cb = __reduce_add_sync(grp, cb);
+  const uint32_t lane = threadIdx.x & 31u;
+  int bx = 0, by = 0, bz = 0, cnt = 1;
+  unsigned long long key = 0ull;
+  long long qx = 0, qy = 0, qz = 0, qd = 0;
+  bool lead = valid;
+  if (valid) {
+    bx = iroundf(px / vs); by = iroundf(py / vs); bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
+    key = bucket_key(bx, by, bz);
+    qx = __float2ll_rn(px * FIXQ); qy = __float2ll_rn(py * FIXQ); qz = __float2ll_rn(pz * FIXQ); qd = __float2ll_rn(dep * FIXQ);
+    if (agg_ok) {  // |q| < 2^26: a 32-lane sum fits int32
+      const unsigned grp = __match_any_sync(vmask, key);
+      lead = lane == (uint32_t)(__ffs(grp) - 1);
+      cnt = __popc(grp);
+      if (cnt > 1) {
+        qx = (long long)__reduce_add_sync(grp, (int)qx);
+        qy = (long long)__reduce_add_sync(grp, (int)qy);
+        qz = (long long)__reduce_add_sync(grp, (int)qz);
+        qd = (long long)__reduce_add_sync(grp, (int)qd);
+        if (tex) {
+          cr = __reduce_add_sync(grp, cr);
+          cg = __reduce_add_sync(grp, cg);
+          cb = __reduce_add_sync(grp, cb);
+        }
       }
     }
-    if (!leader) return -1;
   }
-  uint32_t h = ts_hash(key) & cap_mask;
-  TsBucket* b = nullptr;
-  int fresh = -1;
-  for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
-    TsBucket* c = &tab[h];
-    unsigned long long cur = ts_ld_volatile(&c->key);
-    if (cur == 0ull) {
-      const unsigned long long prev = atomicCAS(&c->key, 0ull, key);
-      if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
-        fresh = (int)h;
-        b = c;
-        break;
+  // find or open the slot
+  uint32_t h = 0;
+  bool fresh = false, found = false;
+  if (lead) {
+    h = slot_hash(bx, by, bz) & cap_mask;
+    for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
+      unsigned long long cur = ts_ld_volatile(&tab[h].key);
+      if (cur == 0ull) {
+        const unsigned long long prev = atomicCAS(&tab[h].key, 0ull, key);
+        if (prev == 0ull) { fresh = true; break; }  // this point opened the bucket: it becomes one ray
+        cur = prev;
       }
-      cur = prev;
+      if (cur == key) { found = true; break; }
+      h = (h + 1) & cap_mask;
     }
-    if (cur == key) { b = c; break; }
-    h = (h + 1) & cap_mask;
+    if (!fresh && !found) { atomicOr(err, TS_ERR_TABLE_FULL); lead = false; }
   }
-  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return -1; }
-  red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
-  red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
-  red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
-  red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
-  red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
-  if (tex) {  // new_pcl_sum_color += rgb (dense_tsdf.py:233-234), exact integer sums
-    red_add_u32(&b->cr, (unsigned int)cr);
-    red_add_u32(&b->cg, (unsigned int)cg);
-    red_add_u32(&b->cb, (unsigned int)cb);
+  // the openers of this warp take consecutive ray indices of their frame (one atomic per warp) and publish them
+  uint32_t r = TS_RAY_PENDING;
+  const unsigned mfresh = __ballot_sync(0xffffffffu, fresh);
+  if (mfresh) {
+    const int l0 = __ffs(mfresh) - 1;
+    int base = 0;
+    if ((int)lane == l0) base = atomicAdd(&n_rays_f[frame], __popc(mfresh));
+    base = __shfl_sync(0xffffffffu, base, l0);
+    if (fresh) {
+      const uint32_t idx = (uint32_t)base + (uint32_t)__popc(mfresh & ((1u << lane) - 1u));
+      if (idx < ray_cap_f) {
+        r = ray_base + idx;
+        bdata[r].slot = tab_base + h;
+        bdata[r].frame = frame;
+        __threadfence();
+      } else {  // cannot happen: every bucket holds at least one pixel / point of its frame
+        atomicOr(err, TS_ERR_RAYLIST_FULL);
+        r = TS_RAY_DROPPED;
+      }
+      *(volatile uint32_t*)&tab[h].ray = r;
+    }
   }
-  return fresh;
+  if (found) {
+    while ((r = *(volatile uint32_t*)&tab[h].ray) == TS_RAY_PENDING) __nanosleep(20);
+  }
+  if (lead && r < TS_RAY_DROPPED) {
+    TsBucket* b = &bdata[r];
+    red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
+    red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
+    red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
+    red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
+    red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
+    if (tex) {  // new_pcl_sum_color += rgb (dense_tsdf.py:233-234), exact integer sums
+      red_add_u32(&b->cr, (unsigned int)cr);
+      red_add_u32(&b->cg, (unsigned int)cg);
+      red_add_u32(&b->cb, (unsigned int)cb);
+    }
+  }
 }
 
-// CTA-aggregated append of the buckets opened by this CTA (one atomic on the global ray counter per CTA instead
-// of one per ray; the rays of a pixel tile stay contiguous in the list).  Must be reached by all threads.
-__device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_base, unsigned n_valid_warp, uint32_t* ray_list,
-                                                int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
-  __shared__ unsigned int s_cnt[8], s_val[8];
-  __shared__ unsigned int s_base;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned m = __ballot_sync(0xffffffffu, fresh_slot >= 0);
-  if (lane == 0) { s_cnt[wid] = __popc(m); s_val[wid] = n_valid_warp; }
+// valid-pixel statistics: one reduction per CTA
+__device__ __forceinline__ void count_valid_cta(unsigned n_valid_warp, TsCounters* ctr) {
+  __shared__ unsigned int s_val;
+  if (threadIdx.x == 0) s_val = 0u;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned tot = 0, nv = 0;
-    for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; nv += s_val[w]; }
-    s_base = tot ? (unsigned)atomicAdd(n_rays, (int)tot) : 0u;
-    if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
-  }
+  if ((threadIdx.x & 31) == 0 && n_valid_warp) atomicAdd(&s_val, n_valid_warp);
   __syncthreads();
-  if (fresh_slot >= 0) {
-    const uint32_t p = s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1));
-    if (p < ray_cap) ray_list[p] = tab_base + (uint32_t)fresh_slot; else atomicOr(err, TS_ERR_RAYLIST_FULL);
-  }
+  if (threadIdx.x == 0 && s_val) atomicAdd(&ctr->n_valid, (unsigned long long)s_val);
 }
 
 // ---------------------------------------------------------------------------
@@ -146,8 +166,8 @@ __device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_bas
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int frame_stride, int row_mul, int w, int hh, int ww,
                                                        const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
-                                                       TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
-                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err,
+                                                       TsSlot* slots, uint32_t bucket_cap, TsBucket* bdata, uint32_t ray_cap_f,
+                                                       int* n_rays_f, TsCounters* ctr, int* err,
                                                        const uint8_t* __restrict__ tex, int th, int tw) {
   const int f = blockIdx.z;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -180,16 +200,16 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets + (size_t)f * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err,
-                                      tex != nullptr, cr, cg, cb);
-  append_rays_cta(fresh, (uint32_t)f * bucket_cap, nv, ray_list, n_rays, ray_cap, ctr, err);
+  bucket_accumulate(valid, slots + (size_t)f * bucket_cap, (uint32_t)f * bucket_cap, bucket_cap - 1, bdata, (uint32_t)f * ray_cap_f, ray_cap_f,
+                    n_rays_f, (uint32_t)f, px, py, pz, dep, in.vs, agg_ok != 0, err, tex != nullptr, cr, cg, cb);
+  count_valid_cta(nv, ctr);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
 }
 
 // K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
 __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
-                                                        TsIntrin in, int agg_ok, TsBucket* buckets, uint32_t bucket_cap,
-                                                        uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
+                                                        TsIntrin in, int agg_ok, TsSlot* slots, uint32_t bucket_cap,
+                                                        TsBucket* bdata, uint32_t ray_cap, int* n_rays_f, TsCounters* ctr,
                                                         int* err, const uint8_t* __restrict__ rgb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int cr = 0, cg = 0, cb = 0;
@@ -206,8 +226,9 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
     if (rgb) { cr = rgb[3 * (size_t)t]; cg = rgb[3 * (size_t)t + 1]; cb = rgb[3 * (size_t)t + 2]; }  // :179-182
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err, rgb != nullptr, cr, cg, cb);  // :183/:185
-  append_rays_cta(fresh, 0u, nv, ray_list, n_rays, ray_cap, ctr, err);
+  bucket_accumulate(valid, slots, 0u, bucket_cap - 1, bdata, 0u, ray_cap, n_rays_f, 0u, px, py, pz, len, in.vs, agg_ok != 0, err,
+                    rgb != nullptr, cr, cg, cb);  // :183/:185
+  count_valid_cta(nv, ctr);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
 
@@ -243,9 +264,21 @@ __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
   if (c) atomicAdd(hi, c);
 }
 
+// compact list of the launch's rays for the one-thread-per-ray march below (frame f owns rays [f*cap, f*cap + n_f))
+__global__ void __launch_bounds__(256) k_ray_compact(const int* __restrict__ n_rays_f, int nf, uint32_t ray_cap_f, uint32_t* ray_list,
+                                                      int* n_rays, uint32_t ray_cap) {
+  const int f = blockIdx.y;
+  int pre = 0, tot = 0;
+  for (int q = 0; q < nf; q++) { const int c = n_rays_f[q]; if (q < f) pre += c; tot += c; }
+  const int nme = n_rays_f[f];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nme; i += gridDim.x * 256)
+    if ((uint32_t)(pre + i) < ray_cap) ray_list[pre + i] = (uint32_t)f * ray_cap_f + (uint32_t)i;
+  if (blockIdx.x == 0 && f == 0 && threadIdx.x == 0) *n_rays = tot;
+}
+
 template <bool TEX>
 __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
-                                                              TsBucket* buckets, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
+                                                              TsBucket* buckets, TsSlot* slots, const uint32_t* __restrict__ ray_list,
                                                               const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned int win[];  // [4][4096]: A.lo, A.hi, B.lo, B.hi
   unsigned int* const w_alo = win;
@@ -270,7 +303,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   // control flow is kept WARP-UNIFORM (32 consecutive rays per warp, march to the longest ray, predicated lanes)
   for (uint32_t base = blockIdx.x * RM_THREADS; base < n_rays; base += gridDim.x * RM_THREADS) {
     if (threadIdx.x == 0) {  // window of this round: around the sensor origin of the round's first ray
-      const TsFrame& f0 = batch.f[ray_list[base] >> bucket_shift];
+      const TsFrame& f0 = batch.f[buckets[ray_list[base]].frame];
       s_org[0] = iroundf(f0.T[0] / vs) - RM_WIN / 2;
       s_org[1] = iroundf(f0.T[1] / vs) - RM_WIN / 2;
       s_org[2] = iroundf(f0.T[2] / vs) - RM_WIN / 2;
@@ -286,12 +319,13 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
     uint32_t f = 0;
     if (live) {
       const uint32_t id = ray_list[r];
-      f = id >> bucket_shift;
       TsBucket* bk = &buckets[id];
+      f = bk->frame;
       cnt = bk->cnt;
       sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
       if (TEX) { ccr = bk->cr; ccg = bk->cg; ccb = bk->cb; }
-      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
+      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its slot back empty
+      *reinterpret_cast<uint4*>(&slots[bk->slot]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       uint4* q = reinterpret_cast<uint4*>(bk);
       q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
@@ -624,6 +658,16 @@ __global__ void k_reset_counters(int* a, int* b) {
   if (b) *b = 0;
 }
 
+__global__ void k_slots_init(TsSlot* s, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) *reinterpret_cast<uint4*>(&s[i]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
+}
+// per-launch counters back to zero (n_rays_f: the per-frame ray counters of the bucket kernels)
+__global__ void k_reset_rays(int* n_rays_f, int* n_rays) {
+  if (threadIdx.x < TSLAM_MAX_BATCH) n_rays_f[threadIdx.x] = 0;
+  if (threadIdx.x == 0 && n_rays) *n_rays = 0;
+}
+
 // ---------------------------------------------------------------------------
 // host: create / destroy / reset
 // ---------------------------------------------------------------------------
@@ -745,15 +789,25 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   const int step = m->cfg.recast_step;
   size_t sampled = (size_t)m->cfg.max_image_pixels / ((size_t)step * step) + 1024;
   m->bucket_cap = (uint32_t)next_pow2(sampled + sampled / 2);
+  if (const char* bc = getenv("TSLAM_BUCKET_CAP")) { if (atoi(bc) >= 1024) m->bucket_cap = (uint32_t)next_pow2((size_t)atoi(bc)); }  // experiment
   // the point-cloud path treats the TSLAM_MAX_BATCH per-frame tables as ONE table
   if ((size_t)m->cfg.max_points * 3 / 2 > (size_t)TSLAM_MAX_BATCH * m->bucket_cap) {
     ts_set_error("max_points=%d too large for the bucket workspace", m->cfg.max_points);
     return TSLAM_E_INVALID;
   }
-  TS_CUDA(cudaMalloc(&m->buckets, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
-  TS_CUDA(cudaMemset(m->buckets, 0, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
+  m->ray_cap_f = (uint32_t)sampled;
   m->ray_list_cap = (uint32_t)((size_t)TSLAM_MAX_BATCH * sampled);
   if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
+  {
+    const size_t ns = (size_t)TSLAM_MAX_BATCH * m->bucket_cap;
+    TS_CUDA(cudaMalloc(&m->slots, ns * sizeof(TsSlot)));
+    k_slots_init<<<(unsigned)((ns + 255) / 256), 256>>>(m->slots, ns);
+    TS_CUDA(cudaGetLastError());
+  }
+  TS_CUDA(cudaMalloc(&m->bdata, (size_t)m->ray_list_cap * sizeof(TsBucket)));
+  TS_CUDA(cudaMemset(m->bdata, 0, (size_t)m->ray_list_cap * sizeof(TsBucket)));
+  TS_CUDA(cudaMalloc(&m->n_rays_f, TSLAM_MAX_BATCH * sizeof(int)));
+  TS_CUDA(cudaMemset(m->n_rays_f, 0, TSLAM_MAX_BATCH * sizeof(int)));
   TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
   TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)2 * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));  // double buffered
   {
@@ -832,7 +886,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (m->tex_stage) cudaFree(m->tex_stage);
   if (m->rgb_stage) cudaFree(m->rgb_stage);
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
-  cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
+  cudaFree(m->slots); cudaFree(m->bdata); cudaFree(m->n_rays_f); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
   if (m->march_mode) ts_march_free(m);
@@ -867,6 +921,7 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
     if (g.col) TS_CUDA(cudaMemsetAsync(g.col, 0, nv * 16, st));
   }
   TS_CUDA(cudaMemsetAsync(m->scratch_i, 0, 4 * sizeof(int), st));  // n_blocks, n_dirty, err, n_rays
+  TS_CUDA(cudaMemsetAsync(m->n_rays_f, 0, TSLAM_MAX_BATCH * sizeof(int), st));
   return TSLAM_OK;
 }
 
@@ -951,6 +1006,19 @@ static void ts_fill_frame(tslam_tsdf* m, TsFrame& fr, const float* R9, const flo
 static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                    const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted,
                                    const uint8_t* tex = nullptr, int th = 0, int tw = 0);
+// process_new_pcl (dense_tsdf.py:236-270) for the rays the bucket kernel has just produced (nf frames)
+static int ts_launch_march(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* pe) {
+  if (!m->g.cword && m->march_mode) return ts_march_launch(m, st, batch, nf, pe ? pe + 4 : nullptr);
+  k_ray_compact<<<dim3(8, nf), 256, 0, st>>>(m->n_rays_f, nf, m->ray_cap_f, m->ray_list, m->n_rays, m->ray_list_cap);
+  TS_LAUNCH_CHECK(m);
+  if (m->g.cword)
+    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->ray_list, m->n_rays, m->ray_list_cap, m->counters);
+  else
+    k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->ray_list, m->n_rays,
+                                                                                   m->ray_list_cap, m->counters);
+  TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
 extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                           const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream) {
   return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0);
@@ -980,8 +1048,6 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
   const int step = m->cfg.recast_step;
   const int hh = (int)((double)h / step), ww = (int)((double)w / step);  // range(0, h/step) (dense_tsdf.py:192,194)
   if (hh <= 0 || ww <= 0) return TSLAM_OK;
-  uint32_t bshift = 0;
-  while ((1u << bshift) < m->bucket_cap) bshift++;
   for (int base = 0; base < n_frames; base += TSLAM_MAX_BATCH) {
     const int nf = (n_frames - base < TSLAM_MAX_BATCH) ? (n_frames - base) : TSLAM_MAX_BATCH;
     TsBatch batch;
@@ -1005,22 +1071,14 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
     dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
     const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
-    k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
-                                          m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw);
+    k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->slots, m->bucket_cap, m->bdata,
+                                          m->ray_cap_f, m->n_rays_f, m->counters, m->g.err, tsrc, th, tw);
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-    if (m->g.cword)
-      k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                     m->ray_list_cap, m->counters);
-    else if (m->march_mode) {
-      int rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
-      if (rcm) return rcm;
-    } else
-      k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                                     m->ray_list_cap, m->counters);
-    TS_LAUNCH_CHECK(m);
+    int rcm = ts_launch_march(m, st, batch, nf, pe);
+    if (rcm) return rcm;
     if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
-    k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
+    k_reset_rays<<<1, TSLAM_MAX_BATCH, 0, st>>>(m->n_rays_f, m->n_rays);
     TS_LAUNCH_CHECK(m);
     m->n_integrate_calls++;
     if (flags & TSLAM_F_COMMIT) {
@@ -1056,27 +1114,18 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
     TS_CUDA(cudaMemcpyAsync(m->rgb_stage, rgb, (size_t)n * 3, cudaMemcpyHostToDevice, st));
     csrc = m->rgb_stage;
   }
-  const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
   cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
   const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
-  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
-                                                    m->ray_list_cap, m->counters, m->g.err, csrc);
+  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->slots, cap_total, m->bdata, m->ray_list_cap, m->n_rays_f,
+                                                    m->counters, m->g.err, csrc);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-  if (m->g.cword)
-    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                   m->ray_list_cap, m->counters);
-  else if (m->march_mode) {
-    int rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
-    if (rcm) return rcm;
-  } else
-    k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                    m->ray_list_cap, m->counters);
-  TS_LAUNCH_CHECK(m);
+  int rcm = ts_launch_march(m, st, batch, 1, pe);
+  if (rcm) return rcm;
   if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
-  k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
+  k_reset_rays<<<1, TSLAM_MAX_BATCH, 0, st>>>(m->n_rays_f, m->n_rays);
   TS_LAUNCH_CHECK(m);
   m->n_integrate_calls++;
   if (flags & TSLAM_F_COMMIT) {

@@ -94,15 +94,18 @@ int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, 
  * copies ONE host frame to a device staging slot on an internal copy stream (overlapping the kernels of the
  * previous launch) and records its pose; every TSLAM_MAX_BATCH/2 queued frames (TSLAM_QUEUE_LAUNCH="a,b" in the
  * environment alternates other counts) - or tslam_tsdf_flush, which every reader calls implicitly - are integrated
- * and committed with one launch triple, so the kernels of one half run while the caller hands over the next.  Pageable frames may be reused
- * immediately.  PAGE-LOCKED (pinned / cudaHostRegister'ed) frames are not copied at all: the GPU fetches their
- * sampled rows (every recast_step-th row) straight from host memory a few calls later - half the PCIe bytes for
- * recast_step 2 - so they must stay valid and unchanged until tslam_tsdf_flush has returned and the stream has
- * been synchronised, or until 2*TSLAM_MAX_BATCH further frames have been queued (the call blocks rather than
- * letting the host run further ahead).  TSLAM_ZERO_COPY=0 in the environment restores whole-frame DMA copies. */
+ * and committed with one launch triple, so the kernels of one half run while the caller hands over the next.
+ * The frame has been consumed when the call returns (the reference's semantics: its kernel launch copies the array
+ * synchronously) - pageable memory is staged by the runtime, a page-locked source is awaited.
+ * tslam_tsdf_set_frame_mode(m, 1) (or TSLAM_ZERO_COPY=1 in the environment) opts into BORROWING page-locked frames
+ * instead: they are not copied at all, the GPU fetches their sampled rows (every recast_step-th row) straight from
+ * host memory a few calls later - half the PCIe bytes for recast_step 2, no wait per frame - and they must then stay
+ * valid and unchanged until tslam_tsdf_flush has returned and the stream has been synchronised, or until
+ * 2*TSLAM_MAX_BATCH further frames have been queued (the call blocks rather than letting the host run further ahead). */
 int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
                            const float* T3, int32_t submap, void* stream);
 int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);
+int tslam_tsdf_set_frame_mode(tslam_tsdf_t* m, int borrow_pinned);
 /* Textured maps (texture_enabled).  set_color_camera_intrinsic (mapping_common.py:28-29) + color_same_proj
  * (dense_tsdf.py:16).  The *_tex / *_rgb forms take the colour image uint8 [n_frames,th,tw,3] (channel order as
  * given - DenseTSDF does not swap BGR) or per-point colours uint8 [n,3]; tex == NULL integrates geometry only.

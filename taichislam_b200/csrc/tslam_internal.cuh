@@ -240,23 +240,13 @@ struct TsIntrin {
   int same_proj;   // color_same_proj
 };
 
-// per-frame buckets (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z), two levels:
-//  * TsSlot  - open-addressing table per frame, 16 bytes: bucket key -> ray index (TS_RAY_PENDING until the opener
-//              has published it);
-//  * TsBucket - dense per-ray record with the exact fixed-point sums (2^-20 m), indexed frame * ray_cap_f + open order.
-struct __align__(16) TsSlot {
-  unsigned long long key;  // packed (bx,by,bz)+1, 0 = empty
-  uint32_t ray;
-  uint32_t pad;
-};
-#define TS_RAY_PENDING 0xFFFFFFFFu
-#define TS_RAY_DROPPED 0xFFFFFFFEu
+// per-frame bucket entry (dense_tsdf.py:64-70 new_pcl_count / new_pcl_sum_pos / new_pcl_z),
+// exact fixed-point sums (2^-20 m).  64-byte stride = two 32-byte sectors.
 struct __align__(64) TsBucket {
+  unsigned long long key;  // packed (bx,by,bz)+1, 0 = empty
   long long sx, sy, sz, sd;
   int cnt;
   unsigned int cr, cg, cb;  // new_pcl_sum_color: exact integer channel sums
-  uint32_t slot;            // index of the bucket's slot (cleared by the consumer of the ray)
-  uint32_t frame;
   int pad[2];
 };
 
@@ -296,7 +286,9 @@ struct TsMarchCtl {  // device-side control block of one launch (zeroed by k_mar
   int scale_k;       // shared-memory sums are kept in units of 2^-scale_k (k_seg_scan: largest k with max * 2^k < 2^30)
   int ticket;
   unsigned int tmp_cursor;  // next free entry of the segment-list pool
-  int pad;
+  int ray_done;      // rays of the list that already have their record (ray set-up runs once per frame group)
+  int setup_ticket;
+  int pad[3];
 };
 struct TsMarchWs {
   TsRay* rays;         // [ray_list_cap]
@@ -329,18 +321,15 @@ struct tslam_tsdf {
   TsIntrin in;
   size_t table_cap;
   // integrate workspace
-  TsSlot* slots;       // [TSLAM_MAX_BATCH * bucket_cap]
-  uint32_t bucket_cap; // slots per frame, power of two
-  TsBucket* bdata;     // [ray_list_cap] dense per-ray sums: frame f owns [f * ray_cap_f, (f + 1) * ray_cap_f)
-  uint32_t ray_cap_f;  // rays per frame (= sampled pixels: every bucket holds at least one)
-  int* n_rays_f;       // [TSLAM_MAX_BATCH] device counters: buckets opened per frame of the launch
-  uint32_t* ray_list;  // [ray_list_cap] compact list of ray indices (legacy / textured march only)
+  TsBucket* buckets;   // [TSLAM_MAX_BATCH * bucket_cap]
+  uint32_t bucket_cap; // power of two
+  uint32_t* ray_list;  // [TSLAM_MAX_BATCH * max_rays_per_frame]
   uint32_t ray_list_cap;
-  int* n_rays;         // device counter of ray_list
+  int* n_rays;         // device counter
   uint16_t* depth_stage;  // device staging for host depth input [TSLAM_MAX_BATCH * max_image_pixels]
   uint8_t* tex_stage;     // device staging for host textures [2 * TSLAM_MAX_BATCH * max_image_pixels * 3] (texture_enabled only)
   uint8_t* rgb_stage;     // device staging for point-cloud colours
-  unsigned int frame_seq; // frames integrated so far (saturates at 2^22-1)
+  unsigned int frame_seq; // frames integrated since the last renormalisation of the colour words (ts_seq_renorm)
   int q_th, q_tw, q_has_tex;
   // pinned host frames are not copied: q_hptr[q] = their device alias; the sampled rows are fetched over PCIe by
   // k_gather_rows in groups of TS_GATHER_GROUP frames (q_gathered = frames already handed to a gather launch)
@@ -371,6 +360,7 @@ struct tslam_tsdf {
   TsMarchWs mw;        // block-binned ray march workspace (tslam_march.cu)
   int march_mode;      // 0 = legacy k_raymarch, 1 = block-binned (default for untextured maps), env TSLAM_MARCH
   int march_verify;    // TSLAM_MARCH_VERIFY=1: every fast-path index is re-computed exactly, mismatches counted
+  int frame_group;     // frames per bucket / ray-set-up round of an integrate launch (TSLAM_FRAME_GROUP, default 8)
   bool clamp_on_commit;
   // frame queue of the per-frame API (tslam_tsdf_queue_depth): double-buffered device staging fed by a copy stream
   int q_n, q_buf, q_h, q_w;
@@ -412,7 +402,7 @@ struct tslam_octo {
   uint16_t* depth_stage;
   float* points_stage;
   uint8_t* tex_stage;     // texture_enabled: device staging of a host colour image / point colours
-  unsigned int frame_seq; // integrate calls so far (saturates at 2^22-1)
+  unsigned int frame_seq; // integrate calls so far
   float* pose_R;
   float* pose_T;
   int* scratch_i;
@@ -458,7 +448,9 @@ int ts_cuda_fail(cudaError_t e, const char* what);
 // shared across translation units
 int ts_flush_pending(tslam_tsdf* m, cudaStream_t st);   // commit if anything is pending
 int ts_check_deferred(tslam_tsdf* m);                    // read + translate device error flags (synchronises)
+int ts_check_deferred_async(tslam_tsdf* m, cudaStream_t st);  // same, after the work queued on st
 // tslam_march.cu: block-binned ray march of the rays listed in m->ray_list (replaces k_raymarch<false>)
 int ts_march_alloc(tslam_tsdf* m);
 void ts_march_free(tslam_tsdf* m);
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* sub_ev);
+int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, int g0);  // rays listed since the last call
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEvent_t* sub_ev);

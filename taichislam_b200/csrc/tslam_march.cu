@@ -35,8 +35,6 @@
 
 #define FULL 0xffffffffu
 #define MS_THREADS 256
-#define MB_THREADS 384
-#define MB_WARPS (MB_THREADS / 32)
 // shared accumulator layout: word index = x*MB_SX + y*MB_SY + z (skewed strides: consecutive samples of a ray
 // spread over the banks whatever its direction - 3.6-way average conflict vs 5.7 for x<<8|y<<4|z)
 #define MB_SX 277
@@ -46,31 +44,32 @@
                                                 // is applied with f32 global reductions instead
 #define MB_SMEM (4 * MB_WORDS * 4)
 #define SEG_CLS 16                               // length classes per block: (count - 1) >> 1
+#define SEG_REP 4                                // counter replicas per (block, class), picked by the walk CTA: the hot
+                                                // blocks' counters would otherwise serialise in one L2 slice
+#define SEG_KEYS (SEG_CLS * SEG_REP)
 
 // ---------------------------------------------------------------------------
 // K2a: ray set-up (process_new_pcl :240-251): one thread per bucket -> one 32-byte ray record
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* bdata, TsSlot* slots,
-                                                    const int* __restrict__ n_rays_f, uint32_t ray_cap_f, TsMarchWs w, TsCounters* ctr) {
-  const uint32_t f = blockIdx.y;
-  const uint32_t nme = min((uint32_t)n_rays_f[f], ray_cap_f);
+__global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* buckets,
+                                                    uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
+                                                    const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr, uint32_t g0) {
+  const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
+  const uint32_t r0 = (uint32_t)w.ctl->ray_done;  // rays of earlier frame groups of this launch
   const float vs = in.vs;
   unsigned int my_rays = 0, my_fmax = 0;
-  const TsFrame& fr = batch.f[f];
-  const int s = fr.submap;
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < nme; i += gridDim.x * 256) {
-    const uint32_t r = f * ray_cap_f + i;
-    TsBucket* bk = &bdata[r];
-    const int4 hd = *reinterpret_cast<const int4*>(&bk->cnt);  // cnt, cr, cg, cb
-    const longlong2 s01 = *reinterpret_cast<const longlong2*>(&bk->sx), s23 = *reinterpret_cast<const longlong2*>(&bk->sz);
-    const uint32_t slot = bk->slot;
-    const int cnt = hd.x;
-    const long long sx = s01.x, sy = s01.y, sz = s23.x, sd = s23.y;
-    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its slot back empty
-    *reinterpret_cast<uint4*>(&slots[slot]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
+  for (uint32_t r = r0 + blockIdx.x * 256 + threadIdx.x; r < n_rays; r += gridDim.x * 256) {
+    const uint32_t id = ray_list[r];
+    const uint32_t f = g0 + (id >> bucket_shift);
+    TsBucket* bk = &buckets[id];
+    const int cnt = bk->cnt;
+    const long long sx = bk->sx, sy = bk->sy, sz = bk->sz, sd = bk->sd;
+    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     uint4* q = reinterpret_cast<uint4*>(bk);
     q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
+    const TsFrame& fr = batch.f[f];
+    const int s = fr.submap;
     TsRay ry;
     ry.ux = ry.uy = ry.uz = ry.L = ry.tx = ry.ty = ry.tz = ry.w = 0.0f;
     int n = 0;
@@ -128,6 +127,11 @@ __global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBat
   if (threadIdx.x == 0) {
     if (s_rays) atomicAdd(&ctr->n_rays, (unsigned long long)s_rays);
     if (s_fmax) atomicMax(&w.ctl->fmax_bits, s_fmax);
+    __threadfence();
+    if (atomicAdd(&w.ctl->setup_ticket, 1) == (int)gridDim.x - 1) {  // last CTA: this group's rays are done
+      w.ctl->setup_ticket = 0;
+      w.ctl->ray_done = (int)n_rays;
+    }
   }
 }
 
@@ -166,15 +170,13 @@ struct WalkSmem {
 };
 
 __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
-                                                             const int* __restrict__ n_rays_f, uint32_t ray_cap_f, TsMarchWs w, TsCounters* ctr) {
+                                                             const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned char ms_smem[];
   WalkSmem& S = *reinterpret_cast<WalkSmem*>(ms_smem);
   for (int e = threadIdx.x; e < RM_TAB; e += MS_THREADS) S.btab[e] = TS_EMPTY;
   if (threadIdx.x == 0) { S.n_chunk = 0; S.cur = 0; S.ovf = 0; }
   __syncthreads();
-  const uint32_t f = blockIdx.y;
-  const uint32_t nme = min((uint32_t)n_rays_f[f], ray_cap_f);
-  const int s = batch.f[f].submap;
+  const uint32_t nme = min((uint32_t)*n_rays_p, ray_cap);
   const uint32_t lane = threadIdx.x & 31u;
   const int max_seg_ray = (int)(in.max_steps * 0.125f) + 8;  // block crossings of the longest ray (+ slack)
   unsigned int my_oob = 0;
@@ -192,17 +194,19 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
     }
     __syncthreads();
     const bool ovf = S.ovf != 0;
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t r = f * ray_cap_f + i;
+    const uint32_t r = base + threadIdx.x;
     float ux = 0.f, uy = 0.f, uz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-    int n = 0;
+    int n = 0, s = 0;
+    uint32_t f = 0;
     bool wide = false;
-    if (i < nme) {
+    if (r < nme) {
       const float4* src = reinterpret_cast<const float4*>(&w.rays[r]);
       const float4 a = src[0], b = src[1];
       ux = a.x; uy = a.y; uz = a.z; tx = b.x; ty = b.y; tz = b.z;
       const uint32_t ax = w.aux[r];
       n = (int)(ax >> 16);
+      f = (ax >> 8) & 255u;
+      s = batch.f[f].submap;
       wide = (ax & TS_AUX_WIDE) != 0;
     }
     int bx, by, bz, sx, sy, sz;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
         else if (cls == 0) my_oob += (unsigned)cnt;
         else {
           const int blk = rm_lookup(g, S.btab, ts_pack_key(s, bx, by, bz), bx, by, bz);  // activates + marks the block dirty
-          if (blk >= 0) key = blk * SEG_CLS + ((cnt - 1) >> 1);  // (< 0: pool exhausted, samples dropped)
+          if (blk >= 0) key = (blk * SEG_CLS + ((cnt - 1) >> 1)) * SEG_REP + (int)(blockIdx.x & (SEG_REP - 1));  // (< 0: pool exhausted)
         }
       }
       const bool rec = key >= 0;
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
     while (j <= n) { const int c = min(n - j + 1, 4095); gen_append(w, g.err, r, j, c); j += c; }
   }
   __syncthreads();
-  const uint32_t cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const uint32_t cta = blockIdx.x;
   uint32_t* cch = w.cta_chunk + (size_t)cta * WK_MAXCH;
   for (int k = threadIdx.x; k < S.n_chunk; k += MS_THREADS) cch[k] = S.chunk[k];
   if (threadIdx.x == 0) w.cta_n[cta] = S.cur;
@@ -287,10 +291,10 @@ __global__ void __launch_bounds__(256) k_seg_class(TsGrid g, TsMarchWs w) {
     const int b = b0 + (int)threadIdx.x;
     unsigned tot = 0;
     if (b < nb && g.dirty_flag[b]) {
-      uint4* c4 = reinterpret_cast<uint4*>(&w.seg_count[(size_t)b * SEG_CLS]);
-      uint4* r4 = reinterpret_cast<uint4*>(&w.seg_rel[(size_t)b * SEG_CLS]);
-#pragma unroll
-      for (int q = 0; q < SEG_CLS / 4; q++) {
+      uint4* c4 = reinterpret_cast<uint4*>(&w.seg_count[(size_t)b * SEG_KEYS]);
+      uint4* r4 = reinterpret_cast<uint4*>(&w.seg_rel[(size_t)b * SEG_KEYS]);
+#pragma unroll 4
+      for (int q = 0; q < SEG_KEYS / 4; q++) {
         const uint4 c = c4[q];
         if ((c.x | c.y | c.z | c.w) == 0u) { continue; }
         r4[q] = make_uint4(tot, tot + c.x, tot + c.x + c.y, tot + c.x + c.y + c.z);
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(1024) k_seg_scan(TsMarchWs w, TsCounters* ctr)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(MS_THREADS) k_seg_place(TsMarchWs w) {
   __shared__ uint32_t s_chunk[WK_MAXCH];
-  const uint32_t cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const uint32_t cta = blockIdx.x;
   const int total = w.cta_n[cta];
   if (total == 0) return;
   const uint32_t lane = threadIdx.x & 31u;
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_seg_place(TsMarchWs w) {
       int c0 = 0;
       if ((int)lane == leader) c0 = atomicAdd(&w.seg_count[key], __popc(grp));
       c0 = __shfl_sync(grp, c0, leader) + __popc(grp & ((1u << lane) - 1u));
-      w.seg[w.seg_off[key / SEG_CLS] + w.seg_rel[key] + (uint32_t)c0] = sg;
+      w.seg[w.seg_off[key / SEG_KEYS] + w.seg_rel[key] + (uint32_t)c0] = sg;
     }
   }
 }
@@ -470,8 +474,8 @@ __device__ __forceinline__ double mb_sum(unsigned int lo, int hi) {
   return (double)((long long)hi * 65536ll + (long long)(unsigned int)(lo - ((unsigned int)hi << 16)));
 }
 
-template <bool VERIFY>
-__global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsMarchWs w,
+template <bool VERIFY, int MB_THREADS, int MB_MINB, bool RET>
+__global__ void __launch_bounds__(MB_THREADS, MB_MINB) k_march_blocks(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsMarchWs w,
                                                                  TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned int mb_smem[];
   unsigned int* const a_lo = mb_smem;
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
         na = __ldg(src); nb = __ldg(src + 1);
       }
     }
+    constexpr int MB_WARPS = MB_THREADS / 32;
     for (int sb = (int)wid * 32; sb < nseg; sb += MB_WARPS * 32) {
       const TsSeg sg = nx;
       const float4 a = na, b = nb;
@@ -576,10 +581,18 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
         if (ok) {
           const int e = lx * MB_SX + ly * MB_SY + lz;
           const int xq = __float2int_rn(avq);
-          atomicAdd(&a_lo[e], (unsigned int)xq);
-          atomicAdd(&a_hi[e], xq >> 16);
-          atomicAdd(&b_lo[e], (unsigned int)wq);
-          atomicAdd(&b_hi[e], wq >> 16);
+          if (RET) {  // lo/hi with carry: two returning atomics + a rare third
+            const unsigned int oa = atomicAdd(&a_lo[e], (unsigned int)xq);
+            const int ca = (xq >> 31) + ((oa + (unsigned int)xq) < oa ? 1 : 0);
+            if (ca) atomicAdd(&a_hi[e], ca);
+            const unsigned int ob = atomicAdd(&b_lo[e], (unsigned int)wq);
+            if ((ob + (unsigned int)wq) < ob) atomicAdd(&b_hi[e], 1);
+          } else {
+            atomicAdd(&a_lo[e], (unsigned int)xq);
+            atomicAdd(&a_hi[e], xq >> 16);
+            atomicAdd(&b_lo[e], (unsigned int)wq);
+            atomicAdd(&b_hi[e], wq >> 16);
+          }
           my_upd++;
         }
         kf += 1.0f;
@@ -602,7 +615,8 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
       const unsigned int alo = a_lo[e];
       const int ahi = a_hi[e];
       a_lo[e] = 0u; a_hi[e] = 0; b_lo[e] = 0u; b_hi[e] = 0;
-      red_add_f32x2(&acc[v], (float)(mb_sum(alo, ahi) * unfix), (float)(mb_sum(blo, bhi) * unfix));
+      if (RET) red_add_f32x2(&acc[v], (float)(((double)ahi * 4294967296.0 + (double)alo) * unfix), (float)(((double)bhi * 4294967296.0 + (double)blo) * unfix));
+      else red_add_f32x2(&acc[v], (float)(mb_sum(alo, ahi) * unfix), (float)(mb_sum(blo, bhi) * unfix));
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -612,12 +626,24 @@ __global__ void __launch_bounds__(MB_THREADS, 2) k_march_blocks(const __grid_con
     my_fb += __shfl_xor_sync(FULL, my_fb, o);
     my_bad += __shfl_xor_sync(FULL, my_bad, o);
   }
+  // one global reduction per CTA and counter (same-address atomics serialise in L2)
+  __shared__ unsigned int s_stat[5];
+  if (threadIdx.x < 5) s_stat[threadIdx.x] = 0u;
+  __syncthreads();
   if (lane == 0) {
-    if (my_upd) atomicAdd(&ctr->n_updates, (unsigned long long)my_upd);
-    if (my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
-    if (my_slow) atomicAdd(&ctr->n_slow, (unsigned long long)my_slow);
-    if (my_fb) atomicAdd(&ctr->n_fallback, (unsigned long long)my_fb);
-    if (my_bad) atomicAdd(&ctr->n_verify_bad, (unsigned long long)my_bad);
+    if (my_upd) atomicAdd(&s_stat[0], my_upd);
+    if (my_oob) atomicAdd(&s_stat[1], my_oob);
+    if (my_slow) atomicAdd(&s_stat[2], my_slow);
+    if (my_fb) atomicAdd(&s_stat[3], my_fb);
+    if (my_bad) atomicAdd(&s_stat[4], my_bad);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_stat[0]) atomicAdd(&ctr->n_updates, (unsigned long long)s_stat[0]);
+    if (s_stat[1]) atomicAdd(&ctr->n_oob, (unsigned long long)s_stat[1]);
+    if (s_stat[2]) atomicAdd(&ctr->n_slow, (unsigned long long)s_stat[2]);
+    if (s_stat[3]) atomicAdd(&ctr->n_fallback, (unsigned long long)s_stat[3]);
+    if (s_stat[4]) atomicAdd(&ctr->n_verify_bad, (unsigned long long)s_stat[4]);
   }
 }
 
@@ -657,8 +683,8 @@ __global__ void __launch_bounds__(256) k_march_generic(const __grid_constant__ T
 // end of a launch: fill cursors back to zero, control block cleared
 __global__ void __launch_bounds__(256) k_march_reset(TsMarchWs w) {
   const int nt = w.ctl->n_touched;
-  for (int q = blockIdx.x * 256 + threadIdx.x; q < nt * (SEG_CLS / 4); q += gridDim.x * 256)
-    reinterpret_cast<uint4*>(w.seg_count + (size_t)w.touched[q / (SEG_CLS / 4)] * SEG_CLS)[q % (SEG_CLS / 4)] = make_uint4(0u, 0u, 0u, 0u);
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < nt * (SEG_KEYS / 4); q += gridDim.x * 256)
+    reinterpret_cast<uint4*>(w.seg_count + (size_t)w.touched[q / (SEG_KEYS / 4)] * SEG_KEYS)[q % (SEG_KEYS / 4)] = make_uint4(0u, 0u, 0u, 0u);
   // the last CTA to finish clears the control block
   __shared__ int s_last;
   __syncthreads();
@@ -688,9 +714,9 @@ int ts_march_alloc(tslam_tsdf* m) {
   TS_CUDA(cudaMalloc(&w.seg, sc * sizeof(TsSeg)));
   TS_CUDA(cudaMalloc(&w.tmp_seg, sc * sizeof(TsSeg)));
   TS_CUDA(cudaMalloc(&w.tmp_key, sc * 4));
-  TS_CUDA(cudaMalloc(&w.seg_count, nb * SEG_CLS * 4));
-  TS_CUDA(cudaMemset(w.seg_count, 0, nb * SEG_CLS * 4));
-  TS_CUDA(cudaMalloc(&w.seg_rel, nb * SEG_CLS * 4));
+  TS_CUDA(cudaMalloc(&w.seg_count, nb * SEG_KEYS * 4));
+  TS_CUDA(cudaMemset(w.seg_count, 0, nb * SEG_KEYS * 4));
+  TS_CUDA(cudaMalloc(&w.seg_rel, nb * SEG_KEYS * 4));
   TS_CUDA(cudaMalloc(&w.seg_off, nb * 4));
   TS_CUDA(cudaMalloc(&w.touched, nb * 4));
   TS_CUDA(cudaMalloc(&w.blk_total, nb * 4));
@@ -717,8 +743,9 @@ int ts_march_alloc(tslam_tsdf* m) {
   const char* ee = getenv("TSLAM_NEAR_EPS");
   if (ee) eps = atof(ee);
   w.near_eps = (float)eps;
-  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
-  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false, 320, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false, 320, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<true, 320, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
   return TSLAM_OK;
 }
 
@@ -729,28 +756,34 @@ void ts_march_free(tslam_tsdf* m) {
   cudaFree(w.cta_chunk);
 }
 
-// nf = frames of the launch (their rays sit in bdata[f * ray_cap_f ...]).
-// sub_ev (profiling, may be null): 4 events recorded after ray set-up, walk + class + scan, placement and the march kernels
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* sub_ev) {
-  const int sms = m->sm_count;
-  const int gx = nf > 1 ? (sms * 3 + nf - 1) / nf : m->mw.walk_x_max;  // CTAs per frame: ~3 per SM over the launch
-  const uint32_t cap_f = nf > 1 ? m->ray_cap_f : m->ray_list_cap;       // (a point cloud is one frame of up to max_points rays)
-  k_ray_setup<<<dim3(gx * 2, nf), 256, 0, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->n_rays_f, cap_f, m->mw, m->counters);
+// ray set-up of the rays listed since the last call (one frame group; g0 = its first frame)
+int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, int g0) {
+  k_ray_setup<<<m->sm_count * 16, 256, 0, st>>>(batch, m->in, m->g, m->buckets, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters,
+                                                (uint32_t)g0);
   TS_LAUNCH_CHECK(m);
+  return TSLAM_OK;
+}
+
+// sub_ev (profiling, may be null): 4 events recorded at the start, after walk + class + scan, placement and the march kernels
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEvent_t* sub_ev) {
+  const int sms = m->sm_count;
+  const int gx = m->mw.walk_x_max;
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[0], st));
-  k_seg_walk<<<dim3(gx, nf), MS_THREADS, (int)sizeof(WalkSmem), st>>>(batch, m->in, m->g, m->n_rays_f, cap_f, m->mw, m->counters);
+  k_seg_walk<<<gx, MS_THREADS, (int)sizeof(WalkSmem), st>>>(batch, m->in, m->g, m->n_rays, m->ray_list_cap, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   k_seg_class<<<sms * 2, 256, 0, st>>>(m->g, m->mw);
   TS_LAUNCH_CHECK(m);
   k_seg_scan<<<1, 1024, 0, st>>>(m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[1], st));
-  k_seg_place<<<dim3(gx, nf), MS_THREADS, 0, st>>>(m->mw);
+  k_seg_place<<<gx, MS_THREADS, 0, st>>>(m->mw);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[2], st));
-  const int grid = (sms - m->rm_reserve) * 2;
-  if (m->march_verify) k_march_blocks<true><<<grid, MB_THREADS, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
-  else k_march_blocks<false><<<grid, MB_THREADS, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
+  static const bool vret = getenv("TSLAM_MB_RET") != nullptr;  // A/B: returning lo atomics + carry instead of 4 no-return atomics
+  const int grid = (sms - m->rm_reserve) * 3;
+  if (m->march_verify) k_march_blocks<true, 320, 3, false><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
+  else if (vret) k_march_blocks<false, 320, 3, true><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
+  else k_march_blocks<false, 320, 3, false><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   k_march_generic<<<sms * 2, 256, 0, st>>>(batch, m->in, m->g, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);

@@ -413,6 +413,8 @@ extern "C" int tslam_mc_generate2(tslam_tsdf_t* m, int32_t step, float thres, in
     TS_CUDA(cudaStreamSynchronize(st));
   }
   *n_tri_out = (int64_t)total;
+  rc = ts_check_deferred(m);  // a map that silently stopped growing (pool exhausted) must not be meshed as if complete
+  if (rc) return rc;
   if ((int64_t)total > cap_tri) {
     ts_set_error("marching cubes: %lld triangles > capacity %lld (output saturated)", (long long)total, (long long)cap_tri);
     return TSLAM_E_CAPACITY;

@@ -292,7 +292,7 @@ extern "C" int tslam_octo_set_color_intrinsics(tslam_octo_t* m, double fx, doubl
 
 static void oc_fill_frame(tslam_octo* m, TsFrame& fr, const float* R9, const float* T3, int submap) {
   memcpy(fr.R, R9, 36); memcpy(fr.T, T3, 12); fr.submap = submap;
-  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;
+  if (m->frame_seq < 0xFFFFFFFEu) m->frame_seq++;  // the colour word keeps 40 bits for it (seq << 24 | rgb): no practical limit
   fr.seq = m->frame_seq;
 }
 

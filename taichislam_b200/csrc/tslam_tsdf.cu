@@ -44,117 +44,90 @@ __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz)
            (unsigned long long)(bz + (1 << 20))) + 1ull);
 }
 
-// accumulate one unprojected point per lane into the frame's buckets.  process_point (dense_tsdf.py:227-234) with
-// exact fixed-point sums.  Two levels (round 2): a table of 16-byte SLOTS (key -> ray index) found by hashing, and
-// the DENSE per-ray array `bdata` that holds the sums.  A ray index is handed out when a bucket is opened, in open
-// order - the rays of a pixel tile are neighbours in `bdata`, so the reductions of a frame hit a compact,
-// L2-resident range and every later pass reads the rays sequentially (round 1 kept the sums inside a 64-byte hash
-// entry: 537 MB of tables, every access a random DRAM sector - ncu: k_ray_setup 157 us at 20 G sectors/s).
-// Lanes of a warp that fall into the same bucket (neighbouring pixels usually do) are merged first (match.any +
-// redux): one probe and one set of reductions per distinct bucket per warp instead of per pixel.
-// Must be called by all 32 lanes; `valid` masks lanes without a point.
-__device__ __forceinline__ uint32_t slot_hash(int bx, int by, int bz) {
-  // locality-preserving: a 4x4x2 group of buckets shares one 512-byte run of slots (a surface patch fills ~1/3 of
-  // it), groups are scattered by a multiplicative hash
-  uint32_t g = ((uint32_t)(bx >> 2) * 0x9E3779B1u) ^ ((uint32_t)(by >> 2) * 0x85EBCA77u) ^ ((uint32_t)(bz >> 1) * 0xC2B2AE3Du);
-  g ^= g >> 15;
-  return (g << 5) | (uint32_t)((bx & 3) | ((by & 3) << 2) | ((bz & 1) << 4));
-}
-__device__ __forceinline__ void bucket_accumulate(bool valid, TsSlot* tab, uint32_t tab_base, uint32_t cap_mask, TsBucket* bdata, uint32_t ray_base,
-                                                  uint32_t ray_cap_f, int* n_rays_f, uint32_t frame, float px, float py, float pz, float dep,
-                                                  float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
+// accumulate one unprojected point per lane into the frame's bucket table.
+// process_point (dense_tsdf.py:227-234) with exact fixed-point sums.  Lanes of a warp that fall into
+// the same bucket (neighbouring pixels usually do) are merged first (match.any + redux): one probe and
+// one set of reductions per distinct bucket per warp instead of per pixel.  Must be called by all 32
+// lanes; `valid` masks lanes without a point.  Returns the table slot when this lane OPENED a bucket
+// (the bucket becomes one ray; the caller appends it to the ray list), else -1.
+__device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, float px, float py, float pz, float dep,
+                                                 float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  const uint32_t lane = threadIdx.x & 31u;
-  int bx = 0, by = 0, bz = 0, cnt = 1;
-  unsigned long long key = 0ull;
-  long long qx = 0, qy = 0, qz = 0, qd = 0;
-  bool lead = valid;
-  if (valid) {
-    bx = iroundf(px / vs); by = iroundf(py / vs); bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
-    key = bucket_key(bx, by, bz);
-    qx = __float2ll_rn(px * FIXQ); qy = __float2ll_rn(py * FIXQ); qz = __float2ll_rn(pz * FIXQ); qd = __float2ll_rn(dep * FIXQ);
-    if (agg_ok) {  // |q| < 2^26: a 32-lane sum fits int32
-      const unsigned grp = __match_any_sync(vmask, key);
-      lead = lane == (uint32_t)(__ffs(grp) - 1);
-      cnt = __popc(grp);
-      if (cnt > 1) {
-        qx = (long long)__reduce_add_sync(grp, (int)qx);
-        qy = (long long)__reduce_add_sync(grp, (int)qy);
-        qz = (long long)__reduce_add_sync(grp, (int)qz);
-        qd = (long long)__reduce_add_sync(grp, (int)qd);
-        if (tex) {
-          cr = __reduce_add_sync(grp, cr);
-          cg = __reduce_add_sync(grp, cg);
-          cb = __reduce_add_sync(grp, cb);
-        }
+  if (!valid) return -1;
+  const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
+  const unsigned long long key = bucket_key(bx, by, bz);
+  long long qx = __float2ll_rn(px * FIXQ), qy = __float2ll_rn(py * FIXQ), qz = __float2ll_rn(pz * FIXQ), qd = __float2ll_rn(dep * FIXQ);
+  int cnt = 1;
+  if (agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
+    const unsigned grp = __match_any_sync(vmask, key);
+    const bool leader = (threadIdx.x & 31) == (__ffs(grp) - 1);
+    cnt = __popc(grp);
+    if (cnt > 1) {
+      qx = (long long)__reduce_add_sync(grp, (int)qx);
+      qy = (long long)__reduce_add_sync(grp, (int)qy);
+      qz = (long long)__reduce_add_sync(grp, (int)qz);
+      qd = (long long)__reduce_add_sync(grp, (int)qd);
+      if (tex) {
+        cr = __reduce_add_sync(grp, cr);
+        cg = __reduce_add_sync(grp, cg);
+        cb = __reduce_add_sync(grp, cb);
       }
     }
+    if (!leader) return -1;
   }
-  // find or open the slot
-  uint32_t h = 0;
-  bool fresh = false, found = false;
-  if (lead) {
-    h = slot_hash(bx, by, bz) & cap_mask;
-    for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
-      unsigned long long cur = ts_ld_volatile(&tab[h].key);
-      if (cur == 0ull) {
-        const unsigned long long prev = atomicCAS(&tab[h].key, 0ull, key);
-        if (prev == 0ull) { fresh = true; break; }  // this point opened the bucket: it becomes one ray
-        cur = prev;
+  uint32_t h = ts_hash(key) & cap_mask;
+  TsBucket* b = nullptr;
+  int fresh = -1;
+  for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
+    TsBucket* c = &tab[h];
+    unsigned long long cur = ts_ld_volatile(&c->key);
+    if (cur == 0ull) {
+      const unsigned long long prev = atomicCAS(&c->key, 0ull, key);
+      if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
+        fresh = (int)h;
+        b = c;
+        break;
       }
-      if (cur == key) { found = true; break; }
-      h = (h + 1) & cap_mask;
+      cur = prev;
     }
-    if (!fresh && !found) { atomicOr(err, TS_ERR_TABLE_FULL); lead = false; }
+    if (cur == key) { b = c; break; }
+    h = (h + 1) & cap_mask;
   }
-  // the openers of this warp take consecutive ray indices of their frame (one atomic per warp) and publish them
-  uint32_t r = TS_RAY_PENDING;
-  const unsigned mfresh = __ballot_sync(0xffffffffu, fresh);
-  if (mfresh) {
-    const int l0 = __ffs(mfresh) - 1;
-    int base = 0;
-    if ((int)lane == l0) base = atomicAdd(&n_rays_f[frame], __popc(mfresh));
-    base = __shfl_sync(0xffffffffu, base, l0);
-    if (fresh) {
-      const uint32_t idx = (uint32_t)base + (uint32_t)__popc(mfresh & ((1u << lane) - 1u));
-      if (idx < ray_cap_f) {
-        r = ray_base + idx;
-        bdata[r].slot = tab_base + h;
-        bdata[r].frame = frame;
-        __threadfence();
-      } else {  // cannot happen: every bucket holds at least one pixel / point of its frame
-        atomicOr(err, TS_ERR_RAYLIST_FULL);
-        r = TS_RAY_DROPPED;
-      }
-      *(volatile uint32_t*)&tab[h].ray = r;
-    }
+  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return -1; }
+  red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
+  red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
+  red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
+  red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
+  red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
+  if (tex) {  // new_pcl_sum_color += rgb (dense_tsdf.py:233-234), exact integer sums
+    red_add_u32(&b->cr, (unsigned int)cr);
+    red_add_u32(&b->cg, (unsigned int)cg);
+    red_add_u32(&b->cb, (unsigned int)cb);
   }
-  if (found) {
-    while ((r = *(volatile uint32_t*)&tab[h].ray) == TS_RAY_PENDING) __nanosleep(20);
-  }
-  if (lead && r < TS_RAY_DROPPED) {
-    TsBucket* b = &bdata[r];
-    red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
-    red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
-    red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
-    red_add_u64((unsigned long long*)&b->sz, (unsigned long long)qz);
-    red_add_u64((unsigned long long*)&b->sd, (unsigned long long)qd);
-    if (tex) {  // new_pcl_sum_color += rgb (dense_tsdf.py:233-234), exact integer sums
-      red_add_u32(&b->cr, (unsigned int)cr);
-      red_add_u32(&b->cg, (unsigned int)cg);
-      red_add_u32(&b->cb, (unsigned int)cb);
-    }
-  }
+  return fresh;
 }
 
-// valid-pixel statistics: one reduction per CTA
-__device__ __forceinline__ void count_valid_cta(unsigned n_valid_warp, TsCounters* ctr) {
-  __shared__ unsigned int s_val;
-  if (threadIdx.x == 0) s_val = 0u;
+// CTA-aggregated append of the buckets opened by this CTA (one atomic on the global ray counter per CTA instead
+// of one per ray; the rays of a pixel tile stay contiguous in the list).  Must be reached by all threads.
+__device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_base, unsigned n_valid_warp, uint32_t* ray_list,
+                                                int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err) {
+  __shared__ unsigned int s_cnt[8], s_val[8];
+  __shared__ unsigned int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, fresh_slot >= 0);
+  if (lane == 0) { s_cnt[wid] = __popc(m); s_val[wid] = n_valid_warp; }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0 && n_valid_warp) atomicAdd(&s_val, n_valid_warp);
+  if (threadIdx.x == 0) {
+    unsigned tot = 0, nv = 0;
+    for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; nv += s_val[w]; }
+    s_base = tot ? (unsigned)atomicAdd(n_rays, (int)tot) : 0u;
+    if (nv) atomicAdd(&ctr->n_valid, (unsigned long long)nv);
+  }
   __syncthreads();
-  if (threadIdx.x == 0 && s_val) atomicAdd(&ctr->n_valid, (unsigned long long)s_val);
+  if (fresh_slot >= 0) {
+    const uint32_t p = s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1));
+    if (p < ray_cap) ray_list[p] = tab_base + (uint32_t)fresh_slot; else atomicOr(err, TS_ERR_RAYLIST_FULL);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -166,10 +139,11 @@ __device__ __forceinline__ void count_valid_cta(unsigned n_valid_warp, TsCounter
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int frame_stride, int row_mul, int w, int hh, int ww,
                                                        const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
-                                                       TsSlot* slots, uint32_t bucket_cap, TsBucket* bdata, uint32_t ray_cap_f,
-                                                       int* n_rays_f, TsCounters* ctr, int* err,
-                                                       const uint8_t* __restrict__ tex, int th, int tw) {
-  const int f = blockIdx.z;
+                                                       TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
+                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err,
+                                                       const uint8_t* __restrict__ tex, int th, int tw, int g0) {
+  const int tz = blockIdx.z;    // bucket table of this frame
+  const int f = g0 + tz;        // frame of the batch (g0 > 0: frame groups sharing the first tables, see ts_integrate_depth_impl)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ii = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
   const int jj = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
@@ -200,16 +174,16 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  bucket_accumulate(valid, slots + (size_t)f * bucket_cap, (uint32_t)f * bucket_cap, bucket_cap - 1, bdata, (uint32_t)f * ray_cap_f, ray_cap_f,
-                    n_rays_f, (uint32_t)f, px, py, pz, dep, in.vs, agg_ok != 0, err, tex != nullptr, cr, cg, cb);
-  count_valid_cta(nv, ctr);
+  const int fresh = bucket_accumulate(valid, buckets + (size_t)tz * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err,
+                                      tex != nullptr, cr, cg, cb);
+  append_rays_cta(fresh, (uint32_t)tz * bucket_cap, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
 }
 
 // K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
 __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
-                                                        TsIntrin in, int agg_ok, TsSlot* slots, uint32_t bucket_cap,
-                                                        TsBucket* bdata, uint32_t ray_cap, int* n_rays_f, TsCounters* ctr,
+                                                        TsIntrin in, int agg_ok, TsBucket* buckets, uint32_t bucket_cap,
+                                                        uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
                                                         int* err, const uint8_t* __restrict__ rgb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int cr = 0, cg = 0, cb = 0;
@@ -226,9 +200,8 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
     if (rgb) { cr = rgb[3 * (size_t)t]; cg = rgb[3 * (size_t)t + 1]; cb = rgb[3 * (size_t)t + 2]; }  // :179-182
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  bucket_accumulate(valid, slots, 0u, bucket_cap - 1, bdata, 0u, ray_cap, n_rays_f, 0u, px, py, pz, len, in.vs, agg_ok != 0, err,
-                    rgb != nullptr, cr, cg, cb);  // :183/:185
-  count_valid_cta(nv, ctr);
+  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err, rgb != nullptr, cr, cg, cb);  // :183/:185
+  append_rays_cta(fresh, 0u, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
 
@@ -264,21 +237,9 @@ __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
   if (c) atomicAdd(hi, c);
 }
 
-// compact list of the launch's rays for the one-thread-per-ray march below (frame f owns rays [f*cap, f*cap + n_f))
-__global__ void __launch_bounds__(256) k_ray_compact(const int* __restrict__ n_rays_f, int nf, uint32_t ray_cap_f, uint32_t* ray_list,
-                                                      int* n_rays, uint32_t ray_cap) {
-  const int f = blockIdx.y;
-  int pre = 0, tot = 0;
-  for (int q = 0; q < nf; q++) { const int c = n_rays_f[q]; if (q < f) pre += c; tot += c; }
-  const int nme = n_rays_f[f];
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < nme; i += gridDim.x * 256)
-    if ((uint32_t)(pre + i) < ray_cap) ray_list[pre + i] = (uint32_t)f * ray_cap_f + (uint32_t)i;
-  if (blockIdx.x == 0 && f == 0 && threadIdx.x == 0) *n_rays = tot;
-}
-
 template <bool TEX>
 __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
-                                                              TsBucket* buckets, TsSlot* slots, const uint32_t* __restrict__ ray_list,
+                                                              TsBucket* buckets, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
                                                               const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned int win[];  // [4][4096]: A.lo, A.hi, B.lo, B.hi
   unsigned int* const w_alo = win;
@@ -303,7 +264,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
   // control flow is kept WARP-UNIFORM (32 consecutive rays per warp, march to the longest ray, predicated lanes)
   for (uint32_t base = blockIdx.x * RM_THREADS; base < n_rays; base += gridDim.x * RM_THREADS) {
     if (threadIdx.x == 0) {  // window of this round: around the sensor origin of the round's first ray
-      const TsFrame& f0 = batch.f[buckets[ray_list[base]].frame];
+      const TsFrame& f0 = batch.f[ray_list[base] >> bucket_shift];
       s_org[0] = iroundf(f0.T[0] / vs) - RM_WIN / 2;
       s_org[1] = iroundf(f0.T[1] / vs) - RM_WIN / 2;
       s_org[2] = iroundf(f0.T[2] / vs) - RM_WIN / 2;
@@ -319,13 +280,12 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
     uint32_t f = 0;
     if (live) {
       const uint32_t id = ray_list[r];
+      f = id >> bucket_shift;
       TsBucket* bk = &buckets[id];
-      f = bk->frame;
       cnt = bk->cnt;
       sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
       if (TEX) { ccr = bk->cr; ccg = bk->cg; ccb = bk->cb; }
-      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its slot back empty
-      *reinterpret_cast<uint4*>(&slots[bk->slot]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
+      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       uint4* q = reinterpret_cast<uint4*>(bk);
       q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
@@ -658,16 +618,6 @@ __global__ void k_reset_counters(int* a, int* b) {
   if (b) *b = 0;
 }
 
-__global__ void k_slots_init(TsSlot* s, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) *reinterpret_cast<uint4*>(&s[i]) = make_uint4(0u, 0u, TS_RAY_PENDING, 0u);
-}
-// per-launch counters back to zero (n_rays_f: the per-frame ray counters of the bucket kernels)
-__global__ void k_reset_rays(int* n_rays_f, int* n_rays) {
-  if (threadIdx.x < TSLAM_MAX_BATCH) n_rays_f[threadIdx.x] = 0;
-  if (threadIdx.x == 0 && n_rays) *n_rays = 0;
-}
-
 // ---------------------------------------------------------------------------
 // host: create / destroy / reset
 // ---------------------------------------------------------------------------
@@ -742,7 +692,10 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   const long long nb = (long long)((cfg->N + TS_B - 1) / TS_B + 1);
   const long long nbz = (long long)((cfg->Nz + TS_B - 1) / TS_B + 1);
   long long dense_blocks = nb * nb * nbz * (cfg->is_global_map ? 1 : 4);
-  if (m->cfg.max_blocks <= 0) m->cfg.max_blocks = (int)(dense_blocks < 32768 ? dense_blocks : 32768);
+  // default pool: the dense block count, at least 32768 blocks (2.4 GB: a submap collection keeps growing with every
+  // keyframe - the reference's pointer SNodes grow on demand), at most 131072 (9.4 GB); callers that know better pass
+  // max_blocks.  Exhaustion drops samples and raises a sticky TSLAM_E_POOL_FULL on the next flush / reader.
+  if (m->cfg.max_blocks <= 0) m->cfg.max_blocks = (int)(dense_blocks < 32768 ? 32768 : (dense_blocks > 131072 ? 131072 : dense_blocks));
   if (m->cfg.max_blocks > TS_MAX_BLOCKS) m->cfg.max_blocks = TS_MAX_BLOCKS;
   ts_fill_intrin(m);
   m->clamp_on_commit = true;
@@ -795,19 +748,10 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     ts_set_error("max_points=%d too large for the bucket workspace", m->cfg.max_points);
     return TSLAM_E_INVALID;
   }
-  m->ray_cap_f = (uint32_t)sampled;
+  TS_CUDA(cudaMalloc(&m->buckets, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
+  TS_CUDA(cudaMemset(m->buckets, 0, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
   m->ray_list_cap = (uint32_t)((size_t)TSLAM_MAX_BATCH * sampled);
   if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
-  {
-    const size_t ns = (size_t)TSLAM_MAX_BATCH * m->bucket_cap;
-    TS_CUDA(cudaMalloc(&m->slots, ns * sizeof(TsSlot)));
-    k_slots_init<<<(unsigned)((ns + 255) / 256), 256>>>(m->slots, ns);
-    TS_CUDA(cudaGetLastError());
-  }
-  TS_CUDA(cudaMalloc(&m->bdata, (size_t)m->ray_list_cap * sizeof(TsBucket)));
-  TS_CUDA(cudaMemset(m->bdata, 0, (size_t)m->ray_list_cap * sizeof(TsBucket)));
-  TS_CUDA(cudaMalloc(&m->n_rays_f, TSLAM_MAX_BATCH * sizeof(int)));
-  TS_CUDA(cudaMemset(m->n_rays_f, 0, TSLAM_MAX_BATCH * sizeof(int)));
   TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
   TS_CUDA(cudaMalloc(&m->depth_stage, (size_t)2 * TSLAM_MAX_BATCH * m->cfg.max_image_pixels * 2));  // double buffered
   {
@@ -816,8 +760,11 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     TS_CUDA(cudaStreamCreateWithPriority(&m->copy_stream, cudaStreamNonBlocking, prio_hi));
   }
   {
-    const char* zc = getenv("TSLAM_ZERO_COPY");  // A/B switch: 0 = always DMA-copy whole frames
-    m->zero_copy = (zc && zc[0] == '0') ? 0 : 1;
+    // Page-locked frames are COPIED at call time by default (the reference's semantics: recast_depth_to_map has
+    // consumed the array when it returns).  Borrowing them instead - the GPU reads the sampled rows straight from
+    // host memory a few calls later - is opt-in: tslam_tsdf_set_frame_mode(m, 1) or TSLAM_ZERO_COPY=1.
+    const char* zc = getenv("TSLAM_ZERO_COPY");
+    m->zero_copy = (zc && zc[0] == '1') ? 1 : 0;
     m->trace = getenv("TSLAM_TRACE") != nullptr;
     if (m->trace) {
       for (int i = 0; i < 2; i++)
@@ -863,6 +810,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     const char* mm = getenv("TSLAM_MARCH");
     m->march_mode = (m->cfg.texture_enabled || (mm && mm[0] == 'l') || m->cfg.max_ray_length / m->cfg.voxel_scale > 60000.0) ? 0 : 1;
     m->march_verify = getenv("TSLAM_MARCH_VERIFY") != nullptr;
+    m->frame_group = TSLAM_MAX_BATCH;  // one round per launch (rounds of 4/8/16 frames were measured: no gain, see profiles/r02_march.md)
+    if (const char* fg = getenv("TSLAM_FRAME_GROUP")) { const int v = atoi(fg); if (v >= 1 && v <= TSLAM_MAX_BATCH) m->frame_group = v; }
     if (m->march_mode) { int rcm = ts_march_alloc(m); if (rcm) return rcm; }
   }
   TS_CUDA(cudaFuncSetAttribute(k_raymarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
@@ -886,7 +835,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (m->tex_stage) cudaFree(m->tex_stage);
   if (m->rgb_stage) cudaFree(m->rgb_stage);
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
-  cudaFree(m->slots); cudaFree(m->bdata); cudaFree(m->n_rays_f); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
+  cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
   if (m->march_mode) ts_march_free(m);
@@ -921,7 +870,6 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
     if (g.col) TS_CUDA(cudaMemsetAsync(g.col, 0, nv * 16, st));
   }
   TS_CUDA(cudaMemsetAsync(m->scratch_i, 0, 4 * sizeof(int), st));  // n_blocks, n_dirty, err, n_rays
-  TS_CUDA(cudaMemsetAsync(m->n_rays_f, 0, TSLAM_MAX_BATCH * sizeof(int), st));
   return TSLAM_OK;
 }
 
@@ -990,6 +938,15 @@ int ts_check_deferred(tslam_tsdf* m) {
   return TSLAM_OK;
 }
 
+// same, ordered on `st` (flush / exporters: the error word is read after the kernels that may have raised it)
+int ts_check_deferred_async(tslam_tsdf* m, cudaStream_t st) {
+  int err = 0;
+  TS_CUDA(cudaMemcpyAsync(&err, m->g.err, 4, cudaMemcpyDeviceToHost, st));
+  TS_CUDA(cudaStreamSynchronize(st));
+  if (!err) return TSLAM_OK;
+  return ts_check_deferred(m);
+}
+
 extern "C" int tslam_tsdf_commit(tslam_tsdf_t* m, void* stream) {
   if (!m) return TSLAM_E_INVALID;
   return ts_flush_pending(m, (cudaStream_t)stream);
@@ -999,28 +956,16 @@ static void ts_fill_frame(tslam_tsdf* m, TsFrame& fr, const float* R9, const flo
   memcpy(fr.R, R9, 36);
   memcpy(fr.T, T3, 12);
   fr.submap = submap;
-  if (m->frame_seq < (1u << 22) - 1) m->frame_seq++;  // 1, 2, ... (texture: later frames win)
+  m->frame_seq++;  // 1, 2, ... (texture: later frames win); < 2^22 - TSLAM_MAX_BATCH (ts_seq_renorm runs before that)
   fr.seq = m->frame_seq;
 }
 
 static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                    const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted,
                                    const uint8_t* tex = nullptr, int th = 0, int tw = 0);
-// process_new_pcl (dense_tsdf.py:236-270) for the rays the bucket kernel has just produced (nf frames)
-static int ts_launch_march(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, int nf, cudaEvent_t* pe) {
-  if (!m->g.cword && m->march_mode) return ts_march_launch(m, st, batch, nf, pe ? pe + 4 : nullptr);
-  k_ray_compact<<<dim3(8, nf), 256, 0, st>>>(m->n_rays_f, nf, m->ray_cap_f, m->ray_list, m->n_rays, m->ray_list_cap);
-  TS_LAUNCH_CHECK(m);
-  if (m->g.cword)
-    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->ray_list, m->n_rays, m->ray_list_cap, m->counters);
-  else
-    k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->bdata, m->slots, m->ray_list, m->n_rays,
-                                                                                   m->ray_list_cap, m->counters);
-  TS_LAUNCH_CHECK(m);
-  return TSLAM_OK;
-}
 extern "C" int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                           const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream) {
+  if (m && m->q_n > 0) { int rcq = ts_launch_queue(m, (cudaStream_t)stream); if (rcq) return rcq; }  // frames queued earlier are integrated first
   return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0);
 }
 static int ts_check_tex(tslam_tsdf* m, const uint8_t* tex, int th, int tw) {
@@ -1035,10 +980,30 @@ extern "C" int tslam_tsdf_integrate_depth_tex(tslam_tsdf_t* m, const uint16_t* d
   if (!m) return TSLAM_E_INVALID;
   int rc = ts_check_tex(m, tex, th, tw);
   if (rc) return rc;
+  if (m->q_n > 0) { rc = ts_launch_queue(m, (cudaStream_t)stream); if (rc) return rc; }
   return ts_integrate_depth_impl(m, depth, mem, n_frames, h, w, R9s, T3s, submap_ids, flags, stream, 0, tex, th, tw);
 }
 // rows_compacted: the frames hold only the sampled rows (hh = h/step rows of w pixels each) - the per-frame queue
 // stages them that way with a strided 2-D copy, halving the host->device bytes for recast_step 2.
+// The colour word of a voxel starts with the 22-bit sequence number of the frame that wrote it ("later frame wins").
+// Before the counter could run out (4.2 M frames) every stored word is reset to sequence 0 and counting restarts:
+// any later frame still beats every stored colour, which is all the rule needs.
+__global__ void __launch_bounds__(256) k_cword_renorm(TsGrid g) {
+  const size_t n = (size_t)min(*g.n_blocks, g.max_blocks) * TS_B3;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) g.cword[i] &= (1ull << 42) - 1ull;
+}
+static int ts_seq_renorm(tslam_tsdf* m, cudaStream_t st, int n_new) {
+  if (m->frame_seq + (unsigned)n_new < (1u << 22) - 1u) return TSLAM_OK;
+  if (m->g.cword) {
+    int rc = ts_flush_pending(m, st);
+    if (rc) return rc;
+    k_cword_renorm<<<m->sm_count * 8, 256, 0, st>>>(m->g);
+    TS_LAUNCH_CHECK(m);
+  }
+  m->frame_seq = 0;
+  return TSLAM_OK;
+}
+
 static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int mem, int32_t n_frames, int32_t h, int32_t w,
                                    const float* R9s, const float* T3s, const int32_t* submap_ids, int flags, void* stream, int rows_compacted,
                                    const uint8_t* tex, int th, int tw) {
@@ -1048,8 +1013,11 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
   const int step = m->cfg.recast_step;
   const int hh = (int)((double)h / step), ww = (int)((double)w / step);  // range(0, h/step) (dense_tsdf.py:192,194)
   if (hh <= 0 || ww <= 0) return TSLAM_OK;
+  uint32_t bshift = 0;
+  while ((1u << bshift) < m->bucket_cap) bshift++;
   for (int base = 0; base < n_frames; base += TSLAM_MAX_BATCH) {
     const int nf = (n_frames - base < TSLAM_MAX_BATCH) ? (n_frames - base) : TSLAM_MAX_BATCH;
+    { int rcs = ts_seq_renorm(m, st, nf); if (rcs) return rcs; }
     TsBatch batch;
     for (int q = 0; q < nf; q++) {
       const int sid = submap_ids ? submap_ids[base + q] : 0;
@@ -1058,7 +1026,9 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     }
     const int rows_stored = rows_compacted ? hh : h;
     const uint16_t* src = depth + (size_t)base * rows_stored * w;
-    if (mem == TSLAM_MEM_HOST) {
+    const bool stage0 = mem == TSLAM_MEM_HOST;  // host batches are staged in buffer 0 of the per-frame queue's staging area
+    if (stage0) {
+      if (m->ev_free_valid[0]) TS_CUDA(cudaStreamWaitEvent(st, m->ev_free[0], 0));  // kernels of an earlier queue launch still read it
       TS_CUDA(cudaMemcpyAsync(m->depth_stage, src, (size_t)nf * h * w * 2, cudaMemcpyHostToDevice, st));
       src = m->depth_stage;
     }
@@ -1069,21 +1039,49 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     }
     cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
-    dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
-    const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
-    k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->slots, m->bucket_cap, m->bdata,
-                                          m->ray_cap_f, m->n_rays_f, m->counters, m->g.err, tsrc, th, tw);
+    const int agg_ok = m->cfg.max_ray_length < 30.0 ? 1 : 0;  // 32-lane int32 sums: |p| <= max_ray * sqrt(1 + tan^2) < 64 m even at 60 deg half-FOV
+    if (!m->g.cword && m->march_mode) {
+      // TSLAM_FRAME_GROUP < 64 runs bucket + ray set-up in rounds of that many frames sharing the first bucket tables
+      // (they then stay L2-resident between the kernel that fills them and the one that drains them).  Experiment
+      // knob: measured 4/8/16/64 frames per round -> 0.43/0.32/0.28/0.28 ms for the two kernels, so the default is one round.
+      const int G = m->frame_group;
+      for (int g0 = 0; g0 < nf; g0 += G) {
+        const int ng = nf - g0 < G ? nf - g0 : G;
+        dim3 grid1((ww + 31) / 32, (hh + 7) / 8, ng);
+        k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap,
+                                              m->ray_list, m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw, g0);
+        TS_LAUNCH_CHECK(m);
+        int rcs = ts_march_setup(m, st, batch, bshift, g0);
+        if (rcs) return rcs;
+      }
+      if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
+      int rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
+      if (rcm) return rcm;
+    } else {
+      dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
+      k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
+                                            m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw, 0);
+      TS_LAUNCH_CHECK(m);
+      if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
+      if (m->g.cword)
+        k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                       m->ray_list_cap, m->counters);
+      else
+        k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                                       m->ray_list_cap, m->counters);
+    }
     TS_LAUNCH_CHECK(m);
-    if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-    int rcm = ts_launch_march(m, st, batch, nf, pe);
-    if (rcm) return rcm;
     if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
-    k_reset_rays<<<1, TSLAM_MAX_BATCH, 0, st>>>(m->n_rays_f, m->n_rays);
+    k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
     TS_LAUNCH_CHECK(m);
     m->n_integrate_calls++;
     if (flags & TSLAM_F_COMMIT) {
       int rc = ts_flush_pending(m, st);
       if (rc) return rc;
+    }
+    if (stage0) {  // the queue must not refill buffer 0 before these kernels have read it
+      TS_CUDA(cudaEventRecord(m->ev_free[0], st));
+      m->ev_free_valid[0] = true;
     }
     if (pe) { TS_CUDA(cudaEventRecord(pe[3], st)); m->prof_launches++; }
   }
@@ -1102,6 +1100,7 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
   if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  { int rcs = ts_seq_renorm(m, st, 1); if (rcs) return rcs; }
   TsBatch batch;
   ts_fill_frame(m, batch.f[0], R9, T3, submap);
   const float* src = xyz;
@@ -1114,18 +1113,29 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
     TS_CUDA(cudaMemcpyAsync(m->rgb_stage, rgb, (size_t)n * 3, cudaMemcpyHostToDevice, st));
     csrc = m->rgb_stage;
   }
+  const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
   cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
-  const int agg_ok = m->cfg.max_ray_length < 60.0 ? 1 : 0;
-  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->slots, cap_total, m->bdata, m->ray_list_cap, m->n_rays_f,
-                                                    m->counters, m->g.err, csrc);
+  const int agg_ok = m->cfg.max_ray_length < 30.0 ? 1 : 0;  // 32-lane int32 sums: |p| <= max_ray * sqrt(1 + tan^2) < 64 m even at 60 deg half-FOV
+  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
+                                                    m->ray_list_cap, m->counters, m->g.err, csrc);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-  int rcm = ts_launch_march(m, st, batch, 1, pe);
-  if (rcm) return rcm;
+  if (m->g.cword)
+    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                   m->ray_list_cap, m->counters);
+  else if (m->march_mode) {
+    int rcm = ts_march_setup(m, st, batch, bshift, 0);
+    if (rcm) return rcm;
+    rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
+    if (rcm) return rcm;
+  } else
+    k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+                                                                    m->ray_list_cap, m->counters);
+  TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
-  k_reset_rays<<<1, TSLAM_MAX_BATCH, 0, st>>>(m->n_rays_f, m->n_rays);
+  k_reset_counters<<<1, 1, 0, st>>>(m->n_rays, nullptr);
   TS_LAUNCH_CHECK(m);
   m->n_integrate_calls++;
   if (flags & TSLAM_F_COMMIT) {
@@ -1223,10 +1233,19 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   return TSLAM_OK;
 }
 
+extern "C" int tslam_tsdf_set_frame_mode(tslam_tsdf_t* m, int borrow_pinned) {
+  if (!m) return TSLAM_E_INVALID;
+  if (m->q_n > 0) { ts_set_error("frames are queued: flush before changing the frame mode"); return TSLAM_E_INVALID; }
+  m->zero_copy = borrow_pinned ? 1 : 0;
+  return TSLAM_OK;
+}
+
 extern "C" int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream) {
   if (!m) return TSLAM_E_INVALID;
   m->q_phase = 0;
-  return ts_launch_queue(m, (cudaStream_t)stream);
+  int rc = ts_launch_queue(m, (cudaStream_t)stream);
+  if (rc) return rc;
+  return ts_check_deferred_async(m, (cudaStream_t)stream);
 }
 
 extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, const float* R9,
@@ -1279,10 +1298,20 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
     else
       cudaGetLastError();
   }
-  if (!m->q_hptr[q]) TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+  if (!m->q_hptr[q]) {
+    TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
+    // a pageable source has been staged when the call returns; a page-locked one is read by the DMA engine later,
+    // so the copy is awaited: the caller may reuse its buffer (camera drivers do)
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, depth_host) == cudaSuccess && at.type == cudaMemoryTypeHost) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
+    else cudaGetLastError();
+  }
   if (has_tex) {
     uint8_t* tdst = m->tex_stage + ((size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * th * tw) * 3;
     TS_CUDA(cudaMemcpyAsync(tdst, tex_host, (size_t)th * tw * 3, cudaMemcpyHostToDevice, m->copy_stream));
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, tex_host) == cudaSuccess && at.type == cudaMemoryTypeHost) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
+    else cudaGetLastError();
   }
   memcpy(m->q_R + 9 * q, R9, 36);
   memcpy(m->q_T + 3 * q, T3, 12);
@@ -1524,7 +1553,7 @@ extern "C" int tslam_tsdf_extract_surface(tslam_tsdf_t* m, int32_t submap, int64
                                                      (float)m->cfg.disp_floor, (float)m->cfg.disp_ceiling, m->colormap, cap, xyz,
                                                      rgb, count_dev);
   TS_LAUNCH_CHECK(m);
-  return TSLAM_OK;
+  return ts_check_deferred_async(m, st);
 }
 
 static float h16_round(float x) {  // slice_z is an f16 field (dense_tsdf.py:72)
@@ -1542,7 +1571,7 @@ extern "C" int tslam_tsdf_extract_slice(tslam_tsdf_t* m, int32_t submap, float z
   k_extract_slice<<<m->sm_count * 4, 256, 0, st>>>(m->g, submap, m->cfg.is_global_map, m->pose_R, m->pose_T, m->in.vs, index, dz,
                                                    m->colormap, cap, xyz, val, rgb, count_dev);
   TS_LAUNCH_CHECK(m);
-  return TSLAM_OK;
+  return ts_check_deferred_async(m, st);
 }
 
 // ---------------------------------------------------------------------------

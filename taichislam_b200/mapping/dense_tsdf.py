@@ -131,6 +131,13 @@ class DenseTSDF(BaseMap):
         if rc:
             capi.check(rc)
 
+    def set_frame_borrowing(self, on=True):
+        """Opt in to zero-copy hand-over of PAGE-LOCKED depth frames: they are not copied, the GPU reads their sampled rows
+        from host memory a few calls later, so the caller must leave them untouched until the next reader / flush.
+        Default (off): recast_depth_to_map has consumed the array when it returns, like the reference."""
+        self._flush()
+        capi.check(self._h.L.tslam_tsdf_set_frame_mode(self._h.h, int(bool(on))))
+
     def _stream_ptr(self):
         # raw handle of torch's current stream; the private accessor skips building a Stream object (once per frame)
         if self._raw_stream is not None:

@@ -48,12 +48,17 @@ def test_queue_paths_equal_batched_call(shape, step):
     ref.integrate_depth(frames[32:], Rs[32:], Ts[32:])
     pinned = torch.from_numpy(frames.view(np.int16)).pin_memory().numpy().view(np.uint16)
     a = TsdfHandle(256, 256, **kw)
-    queue_frames(a, list(pinned), Rs, Ts)            # page-locked: row gather when w % 8 == 0 and step >= 2, else copies
+    queue_frames(a, list(pinned), Rs, Ts)            # page-locked, default mode: copied (and awaited) at call time
     same_map(a, ref)
+    a2 = TsdfHandle(256, 256, **kw)
+    assert a2.L.tslam_tsdf_set_frame_mode(a2.h, 1) == 0
+    queue_frames(a2, list(pinned), Rs, Ts)           # borrowed: row gather when w % 8 == 0 and step >= 2, else copies
+    same_map(a2, ref)
     b = TsdfHandle(256, 256, **kw)
     queue_frames(b, [f.copy() for f in frames], Rs, Ts)  # pageable: DMA copies
     same_map(b, ref)
     c = TsdfHandle(256, 256, **kw)
+    assert c.L.tslam_tsdf_set_frame_mode(c.h, 1) == 0
     mixed = [pinned[q] if q % 3 else frames[q].copy() for q in range(n)]  # both kinds inside one launch
     queue_frames(c, mixed, Rs, Ts)
     same_map(c, ref)
@@ -82,6 +87,59 @@ def test_queue_geometry_change_and_reset():
     ref.reset()
     ref.integrate_depth(big, Rs[:5], Ts[:5])
     same_map(a, ref)
+
+
+def test_pinned_frame_may_be_reused_right_after_the_call():
+    """Default frame mode = the reference's semantics: recast_depth_to_map has consumed the array when it returns
+    (its kernel launch copies it synchronously), so a camera driver may refill ONE page-locked buffer per frame.
+    (Borrowing - tslam_tsdf_set_frame_mode(m, 1) - trades that guarantee for zero copies; include/tslam.h.)"""
+    import torch
+    from taichislam_b200 import _capi as capi
+    from taichislam_b200.tsdf_handle import TsdfHandle
+    kw = dict(K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    n = 12
+    rng = np.random.default_rng(5)
+    frames = np.clip(syn.scene_room().astype(np.int32)[None] + rng.integers(-60, 61, (n, 480, 640)), 0, 65535).astype(np.uint16)
+    Rs, Ts = syn.stream_poses(n, start=3)
+    ref = TsdfHandle(256, 256, **kw)
+    ref.integrate_depth(frames, Rs, Ts)
+    g = TsdfHandle(256, 256, **kw)
+    buf = torch.zeros((480, 640), dtype=torch.int16).pin_memory().numpy().view(np.uint16)  # the one buffer of a "driver"
+    for q in range(n):
+        buf[:] = frames[q]
+        R9, T3 = capi.f32c(Rs[q]).reshape(9), capi.f32c(Ts[q]).reshape(3)
+        capi.check(g.L.tslam_tsdf_queue_depth(g.h, buf.ctypes.data_as(C.c_void_p), 480, 640, capi.np_ptr(R9), capi.np_ptr(T3), 0, capi.stream_ptr()))
+        buf[:] = 0  # scribble over it at once
+    capi.check(g.L.tslam_tsdf_flush(g.h, capi.stream_ptr()))
+    g.sync()
+    same_map(g, ref)
+
+
+def test_queued_frames_then_host_batch():
+    """A host batch issued while frames are queued: the queued frames are integrated first (frame order decides the
+    colour / Wmax rules) and the batch's staging copy must not clobber them (shared staging buffer)."""
+    from taichislam_b200 import _capi as capi
+    from taichislam_b200.tsdf_handle import TsdfHandle
+    kw = dict(K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    rng = np.random.default_rng(11)
+    frames = np.clip(syn.scene_room().astype(np.int32)[None] + rng.integers(-60, 61, (9, 480, 640)), 0, 65535).astype(np.uint16)
+    Rs, Ts = syn.stream_poses(9, start=20)
+    ref = TsdfHandle(256, 256, **kw)
+    ref.integrate_depth(frames[:5], Rs[:5], Ts[:5])
+    ref.integrate_depth(frames[5:], Rs[5:], Ts[5:])
+    g = TsdfHandle(256, 256, **kw)
+    for q in range(5):
+        R9, T3 = capi.f32c(Rs[q]).reshape(9), capi.f32c(Ts[q]).reshape(3)
+        f = frames[q].copy()
+        capi.check(g.L.tslam_tsdf_queue_depth(g.h, f.ctypes.data_as(C.c_void_p), 480, 640, capi.np_ptr(R9), capi.np_ptr(T3), 0, capi.stream_ptr()))
+    g.integrate_depth(frames[5:], Rs[5:], Ts[5:])   # host batch, no flush in between
+    for q in range(3):  # and the queue keeps working afterwards
+        R9, T3 = capi.f32c(Rs[q]).reshape(9), capi.f32c(Ts[q]).reshape(3)
+        f = frames[q].copy()
+        capi.check(g.L.tslam_tsdf_queue_depth(g.h, f.ctypes.data_as(C.c_void_p), 480, 640, capi.np_ptr(R9), capi.np_ptr(T3), 0, capi.stream_ptr()))
+    capi.check(g.L.tslam_tsdf_flush(g.h, capi.stream_ptr()))
+    ref.integrate_depth(frames[:3], Rs[:3], Ts[:3])
+    same_map(g, ref)
 
 
 def test_queue_and_batch_argument_errors():

@@ -276,3 +276,43 @@ def test_block_axis_10_and_long_range_config():
     # TSDF values reach 64 m here: the 1e-4 bar of the default configuration (values <= 10 m) scales with the
     # magnitude of the f32 sums (relative 2e-5 observed at the voxels next to the sensor, thousands of contributions)
     compare_voxels(g2.gather(), o2.gather(), 2e-3)
+
+
+def _march_run(monkeypatch, env, scene="room"):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    d = {"room": syn.scene_room(), "noise": syn.scene_noise()}[scene]
+    n = 3
+    Rs, Ts = syn.stream_poses(n, start=11)
+    g, o = make_pair([25.6, 25.6], is_global_map=True)
+    g.integrate_depth(np.stack([d] * n), Rs, Ts)
+    for q in range(n):
+        o.integrate_depth(Rs[q], Ts[q], d, commit=(q == n - 1))
+    return g, o
+
+
+def test_binned_march_fast_index_is_exact(monkeypatch):
+    """The block-binned march takes a voxel index from ONE fused multiply-add per axis when the fraction is at least
+    near_eps from .5, and recomputes round((u*j*vs + T)/vs) literally otherwise.  TSLAM_MARCH_VERIFY=1 recomputes
+    every index: not one fast-path index may differ (n_verify_bad), and the exact path must be the rare one."""
+    g, o = _march_run(monkeypatch, {"TSLAM_MARCH_VERIFY": "1"}, "noise")
+    stats_equal(g, o)
+    compare_voxels(g.gather(), o.gather(), TOL)
+    ms = g.march_stats()
+    assert ms["n_verify_bad"] == 0 and ms["n_segs"] > 0
+    assert ms["n_slow"] < 0.01 * g.stats()["n_updates"]
+
+
+def test_binned_march_overflow_and_legacy_paths_agree(monkeypatch):
+    """(a) segment workspace too small -> the rays that do not fit take the exact one-reduction-per-sample path;
+    (b) TSLAM_MARCH=legacy, the round-1 kernel.  Both must build the map of the default path."""
+    g0, o = _march_run(monkeypatch, {})
+    ref = g0.gather()
+    compare_voxels(ref, o.gather(), TOL)
+    g1, _ = _march_run(monkeypatch, {"TSLAM_SEG_CAP": "20000"})
+    assert g1.march_stats()["n_generic"] > 0
+    compare_voxels(g1.gather(), ref, TOL)
+    monkeypatch.delenv("TSLAM_SEG_CAP")
+    g2, _ = _march_run(monkeypatch, {"TSLAM_MARCH": "legacy"})
+    assert g2.march_stats()["n_segs"] == 0
+    compare_voxels(g2.gather(), ref, TOL)

@@ -1,14 +1,17 @@
 #!/usr/bin/env python3
 """bench.py - depth frames/s into a 512^3 TSDF (BASELINE.json metric) on N B200s.
 
-A "step" = one pass of the hot path over one batch of 64 synthetic 640x480 depth frames:
-bucket kernel -> ray-march kernel -> commit kernel (all of dense_tsdf.py:162-270 for the
-batch), state fully materialised at the end of every step.
+A "step" = one pass of the hot path over 1024 synthetic 640x480 depth frames (16 launches of 64 frames each:
+bucket kernel -> ray-march kernels -> commit kernel = all of dense_tsdf.py:162-270), state fully materialised at
+the end of every launch.  Every frame of the stream has its own depth image (sphere radius varies with the frame
+index) and its own pose.
 
   value        frames/s with the depth frames already resident in HBM (whole job, all ranks)
-  e2e          frames/s through the public Python API (taichislam_b200.mapping.DenseTSDF) from
-               pinned HOST frames: H2D copy of every frame and a D2H read of the step's counters
-               inside the timed region
+  e2e          frames/s through the public Python API (taichislam_b200.mapping.DenseTSDF.recast_depth_to_map,
+               one call per frame) from pinned HOST frames in the DEFAULT frame mode (the frame is copied - and the
+               copy awaited - inside the call, the reference's semantics); H2D copy of every frame and a D2H read of
+               the step's counters inside the timed region.  extras.e2e_modes adds the opt-in borrowing mode (the GPU
+               reads the sampled rows of page-locked frames itself) and pageable frames.
   roofline     ray-march kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
   cpu_baseline the CPU oracle (restatement of the reference's Taichi kernels; Taichi itself is
                not installable here) on all host cores, bounded sample, rank 0 only
@@ -32,8 +35,13 @@ if ROOT not in sys.path:
 
 METRIC = "depth_frames_per_sec_into_512^3_tsdf"
 UNIT = "frames/s"
-BATCH = 64              # frames per step (= TSLAM_MAX_BATCH: one launch triple per step)
+BATCH = 64              # frames per integrate launch (= TSLAM_MAX_BATCH)
+LAUNCHES_PER_STEP = 16  # one step = 1024 frames, ~10 ms of GPU work
+STEP_FRAMES = BATCH * LAUNCHES_PER_STEP
 POOL_BATCHES = 4        # distinct input batches cycled through: 4*64*614 KB = 157 MB > 126 MB L2
+WORKLOAD = ("C2: synthetic 640x480 uint16 depth stream (S2: camera-centred sphere, R = 4 m +- 0.2 m varying with the frame "
+            "index, circle poses) -> 512^3 TSDF, voxel 0.05 m, recast_step 2, max_ray 10 m")
+CONFIG = {"workload": WORKLOAD, "frames_per_step": STEP_FRAMES, "frames_per_launch": BATCH, "grid": "512^3"}
 MAP_SCALE = [25.6, 25.6]  # 512^3 voxels of 0.05 m (C2)
 
 
@@ -171,9 +179,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_SPHERES = {}
+
+
+def frame_depth(t):
+    """Depth image of stream frame t: the S2 sphere with a radius that depends on t (11 distinct images)."""
+    from taichislam_b200 import synthetic as syn
+    k = ((t % 256) * 7) % 11
+    if k not in _SPHERES:
+        _SPHERES[k] = syn.scene_sphere(4.0 + 0.04 * (k - 5))
+    return _SPHERES[k]
+
+
 def make_inputs(n_frames, start):
     from taichislam_b200 import synthetic as syn
-    depth = np.broadcast_to(syn.scene_sphere(4.0), (n_frames, syn.H, syn.W))
+    depth = np.stack([frame_depth(start + q) for q in range(n_frames)]) if n_frames else np.zeros((0, syn.H, syn.W), np.uint16)
     Rs, Ts = syn.stream_poses(n_frames, start=start)
     return depth, Rs, Ts
 
@@ -197,7 +217,7 @@ def cpu_baseline(target_seconds=12.0):
     integrate_stream_mt(maps, d, Rs, Ts)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} frames of the S2 stream (sphere R=4 m, circle poses) into {cores} independent 512^3 maps, "
+            "sample": f"{n} frames of the same stream into {cores} independent 512^3 maps, "
                       f"one host thread each, {dt:.1f} s; oracle = CPU restatement of the reference's Taichi kernels "
                       f"(taichi not installable)"}
 
@@ -224,27 +244,90 @@ def run_reference(args, rank, world):
         t += per_step
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt
-    sample = (f"{per_step} frames/step of the S2 stream into {cores} independent 512^3 maps, {cores} host threads; "
-              "CPU restatement of the reference (taichi cannot be installed: no wheel, no network)")
+    sample = (f"{per_step} frames per step (bounded sample of the {STEP_FRAMES}-frame step) of the same stream into {cores} independent "
+              f"512^3 maps, {cores} host threads; CPU restatement of the reference (taichi cannot be installed: no wheel, no network)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: synthetic 640x480 depth stream (S2 sphere R=4 m) -> 512^3 TSDF", "frames_per_step": per_step},
+        "config": dict(CONFIG),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
+def frame_depth_mod(t):
+    return frame_depth(t % 256)
+
+
+def c5_extras(rank, local_rank, world, dist, torch):
+    """BASELINE config 5 flavour on the bench's ranks: 64 submaps (10 frames each) integrated submap-sharded, fused into
+    a 2048^3 x 0.05 m global volume TILED over the ranks (data-driven tiling, foreign blocks in one NCCL all-to-all,
+    one-block halo, local marching cubes, mesh-vertex all-gather).  Everything is run twice; the second (warm) pass is
+    timed on the device (CUDA events, max over ranks)."""
+    from taichi_slam.mapping import DenseTSDF, MarchingCubeMesher
+    from taichislam_b200 import synthetic as syn
+    from taichislam_b200.distributed import TiledGlobalMap, submap_owner
+    n_sub, frames_per = 64, 10
+    sub = DenseTSDF(map_scale=[25.6, 25.6], voxel_scale=0.05, max_submap_num=64, max_disp_particles=1024, max_blocks=40000)
+    sub.set_dep_camera_intrinsic(syn.K_DEPTH)
+    glo = DenseTSDF(map_scale=[102.4, 102.4], voxel_scale=0.05, is_global_map=True, max_submap_num=64, max_disp_particles=1024,
+                    max_blocks=60000)
+    mine = [s_ for s_ in range(n_sub) if submap_owner(s_, world) == rank]
+    for s_ in range(n_sub):
+        gx, gy = s_ % 8, s_ // 8
+        a = 0.3 * s_
+        Rb = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+        glo.set_base_pose_submap(s_, Rb, np.array([6.0 * (gx - 3.5), 6.0 * (gy - 3.5), 0.0]))
+    d = syn.scene_sphere(4.0)
+    for s_ in mine:
+        sub.active_submap_id[None] = s_
+        sub.set_base_pose_submap(s_, np.eye(3), np.zeros(3))
+        for q in range(frames_per):
+            R, T = syn.stream_pose(q * 7)
+            sub.recast_depth_to_map(R, T, d, np.array([]))
+    sub._flush()
+    tiled = TiledGlobalMap(glo, dist, rank, world)
+    mesher = MarchingCubeMesher(glo, 3000000, tsdf_surface_thres=0.25)
+
+    def timed(fn):
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    tiled.fuse_submaps_tiled(sub)                      # cold: NCCL channels, allocations
+    tiled.generate_mesh_all_gather(mesher)
+    fuse_ms, _ = timed(lambda: tiled.fuse_submaps_tiled(sub))
+    x = dict(tiled.last_exchange)
+    mesh_ms, (mv, mn, counts) = timed(lambda: tiled.generate_mesh_all_gather(mesher))
+    x.update(tiled.last_exchange)
+    tot = torch.tensor([float(glo.count_active()), float(x["fusion_blocks_sent"]), float(x.get("halo_blocks_sent", 0)),
+                        float(x["fusion_bytes_sent"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    return {"config": "C5: 64 submaps -> 2048^3 x 0.05 m global volume tiled over the ranks", "tiles": list(tiled.tiles),
+            "cuts": [list(map(int, c)) for c in tiled.cuts] if tiled.cuts else None,
+            "fuse_ms": fuse_ms, "mesh_ms": mesh_ms, "global_voxels": int(tot[0].item()),
+            "fusion_blocks_exchanged": int(tot[1].item()), "exchanged_MB": tot[3].item() / 1e6,
+            "halo_blocks_exchanged": int(tot[2].item()), "triangles": int(sum(counts)), "triangles_per_rank": [int(c) for c in counts],
+            "timing": "warm second pass, CUDA events, max over ranks; mesh_ms = halo exchange + local marching cubes + mesh all-gather"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -262,7 +345,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from taichislam_b200 import synthetic as syn
     from taichislam_b200.tsdf_handle import TsdfHandle
-    from oracle.oracle import tsdf_dims  # noqa: F401  (dims helper only; the oracle is not on the measured path)
 
     def barrier():
         if world > 1:
@@ -270,28 +352,27 @@ def main():
         torch.cuda.synchronize()
 
     N, Nz = 512, 512
+    t_rank = rank * 102400  # every rank integrates its own stretch of the stream into its own map (submap sharding); multiple of 256
     # ---- device-resident arm ------------------------------------------------------------------
     g = TsdfHandle(N, Nz, K=syn.K_DEPTH, is_global_map=True)
     pool = []
-    for b in range(POOL_BATCHES):
-        d, _, _ = make_inputs(BATCH, 0)
+    for b in range(POOL_BATCHES):  # frame t of the stream uses image t mod 256: the pool holds exactly those 256 frames
+        d, _, _ = make_inputs(BATCH, t_rank + b * BATCH)
         pool.append(torch.from_numpy(np.ascontiguousarray(d).view(np.int16)).cuda())
-    frame_t = rank * 100000  # every rank integrates its own stretch of the stream into its own map (submap sharding)
+    n_launches = (args.warmup + args.steps) * LAUNCHES_PER_STEP
+    Rs_all, Ts_all = syn.stream_poses(n_launches * BATCH, start=t_rank)   # host pose stream, prepared up front
+    Rs_all = np.ascontiguousarray(Rs_all.astype(np.float32).reshape(n_launches, BATCH, 9))
+    Ts_all = np.ascontiguousarray(Ts_all.astype(np.float32).reshape(n_launches, BATCH, 3))
+    launch_no = [0]
 
-    n_steps_total = args.warmup + args.steps
-    Rs_all, Ts_all = syn.stream_poses(n_steps_total * BATCH, start=frame_t)   # host pose stream, prepared up front
-    Rs_all = np.ascontiguousarray(Rs_all.astype(np.float32).reshape(n_steps_total, BATCH, 9))
-    Ts_all = np.ascontiguousarray(Ts_all.astype(np.float32).reshape(n_steps_total, BATCH, 3))
-    step_no = [0]
-
-    def step_dev(i, t):
-        k = step_no[0]
-        step_no[0] += 1
-        g.integrate_depth(pool[i % POOL_BATCHES], Rs_all[k], Ts_all[k], commit=True)
+    def step_dev():
+        for _ in range(LAUNCHES_PER_STEP):
+            k = launch_no[0]
+            launch_no[0] += 1
+            g.integrate_depth(pool[k % POOL_BATCHES], Rs_all[k], Ts_all[k], commit=True)
 
     for i in range(args.warmup):
-        step_dev(i, frame_t)
-        frame_t += BATCH
+        step_dev()
     g.stats(clear=True)
     g.set_profiling(True)
     l0 = g.launch_count()
@@ -301,32 +382,36 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step_dev(i, frame_t)
-        frame_t += BATCH
+        step_dev()
     e1.record()
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = g.launch_count() - l0
     st = g.stats()
-    kms = g.kernel_ms(min(args.steps, 512))
+    kms = g.kernel_ms2(min(args.steps * LAUNCHES_PER_STEP, 512))
+    mstats = g.march_stats()
     g.sync()
     tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total_max = float(tmax.item())
-    value = world * args.steps * BATCH / (ms_total_max * 1e-3)
+    value = world * args.steps * STEP_FRAMES / (ms_total_max * 1e-3)
 
-    # roofline of the dominant kernel (ray march): SURVEY 8d algorithmic bytes 17*rays + 9*updates per launch
+    # roofline of process_new_pcl (dense_tsdf.py:236-270), SURVEY 8d algorithmic bytes 17*rays + 9*updates per launch,
+    # over the CUDA-event time of ALL its kernels (ray set-up, segment walk / scan / placement, block march); the
+    # dominant one (k_march_blocks) is listed beside it
     peak, peak_src = load_peaks()
-    ray_ms = float(kms[:, 1].mean()) if len(kms) else float("nan")
-    bucket_ms = float(kms[:, 0].mean()) if len(kms) else float("nan")
-    commit_ms = float(kms[:, 2].mean()) if len(kms) else float("nan")
-    rays_per_launch = st["n_rays"] / max(args.steps, 1)
-    upd_per_launch = st["n_updates"] / max(args.steps, 1)
+    km = kms.mean(axis=0) if len(kms) else np.full(7, np.nan)
+    bucket_ms, ray_ms, commit_ms = float(km[0]), float(km[1]), float(km[2])
+    n_l = max(args.steps * LAUNCHES_PER_STEP, 1)
+    rays_per_launch = st["n_rays"] / n_l
+    upd_per_launch = st["n_updates"] / n_l
     bytes_launch = 17.0 * rays_per_launch + 9.0 * upd_per_launch
     achieved = bytes_launch / (ray_ms * 1e-3) / 1e9 if ray_ms == ray_ms and ray_ms > 0 else None
-    frame_bytes = (2.0 * st["n_px"] + 24.0 * st["n_valid"] + 17.0 * st["n_rays"] + 9.0 * st["n_updates"]) / max(args.steps * BATCH, 1)
+    march_only = float(km[6])
+    frame_bytes = (2.0 * st["n_px"] + 24.0 * st["n_valid"] + 17.0 * st["n_rays"] + 9.0 * st["n_updates"]) / max(n_l * BATCH, 1)
+    tr = load_traffic("k_march_blocks") or (None, None)
 
     # ---- marching cubes of the resulting map (C2 "+ marching cubes"), timed outside the frame metric ----
     mc = {}
@@ -339,73 +424,99 @@ def main():
         mc = {"triangles": int(ntri), "ms_incl_d2h_of_mesh": 1e3 * (time.perf_counter() - t1), "first_call_ms": 1e3 * (t1 - t0)}
     except Exception as ex:  # pragma: no cover
         mc = {"error": str(ex)}
+    g.close()
 
-    # ---- end-to-end arm: public API, pinned host frames, H2D + D2H inside the timed region --------
-    e2e = None
+    # ---- end-to-end arm: public API, host frames, H2D + D2H inside the timed region ----------------
+    e2e, e2e_modes = None, {}
     if not args.no_e2e:
-        try:
-            from taichislam_b200.mapping import DenseTSDF
+        from taichislam_b200.mapping import DenseTSDF
+        empty_tex = np.array([])
+        host_t = torch.from_numpy(np.ascontiguousarray(make_inputs(BATCH, t_rank)[0]).view(np.int16))
+
+        def run_e2e(mode, steps):
             m = DenseTSDF(map_scale=MAP_SCALE, voxel_scale=0.05, num_voxel_per_blk_axis=16, is_global_map=True)
             m.set_dep_camera_intrinsic(syn.K_DEPTH)
             m.set_base_pose_submap(0, np.eye(3), np.zeros(3))  # pose-table rows start at zero (mapping_common.py:106-107)
-            host = torch.from_numpy(np.ascontiguousarray(make_inputs(BATCH, 0)[0]).view(np.int16)).pin_memory()
+            if mode == "borrow":
+                m.set_frame_borrowing(True)
+            host = host_t.clone() if mode == "pageable" else host_t.pin_memory()
             host_np = host.numpy().view(np.uint16)
-            empty_tex = np.array([])
-            zero_copy = os.environ.get("TSLAM_ZERO_COPY", "1") != "0"
-            t = rank * 100000 + 50000
-            eRs, eTs = syn.stream_poses(n_steps_total * BATCH, start=t)   # host pose stream prepared up front
+            t = t_rank + 51200
+            eRs, eTs = syn.stream_poses((args.warmup + steps) * STEP_FRAMES, start=t)
             ek = [0]
 
-            def step_e2e():
+            def step():
                 k0 = ek[0]
-                ek[0] += BATCH
-                for q in range(BATCH):
-                    m.recast_depth_to_map(eRs[k0 + q], eTs[k0 + q], host_np[q], empty_tex)
+                ek[0] += STEP_FRAMES
+                for q in range(STEP_FRAMES):
+                    m.recast_depth_to_map(eRs[k0 + q], eTs[k0 + q], host_np[q % BATCH], empty_tex)
                 return m.frame_counters()  # flushes the queue, commits, D2H read of the integrate counters
 
             for i in range(args.warmup):
-                step_e2e()
-            m.frame_counters()
+                step()
             barrier()
             t0 = time.perf_counter()
-            for i in range(args.steps):
-                res = step_e2e()
+            for i in range(steps):
+                res = step()
             barrier()
             dt = time.perf_counter() - t0
             assert res["n_updates"] > 0, "e2e arm integrated nothing"
             tm = torch.tensor([dt], device="cuda", dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            e2e = {"value": world * args.steps * BATCH / float(tm.item()), "unit": UNIT,
-                   # page-locked frames: the GPU fetches the sampled rows (every recast_step-th) over PCIe itself
-                   "h2d_bytes_per_step": int(BATCH * (syn.H // 2) * syn.W * 2) if zero_copy else int(BATCH * syn.H * syn.W * 2),
-                   "d2h_bytes_per_step": int(res["d2h_bytes"]),
-                   "api": "DenseTSDF.recast_depth_to_map per frame (pinned host uint16 frames" +
-                          (", sampled rows read by the GPU from host memory)" if zero_copy else ", whole-frame DMA copies)")}
-        except Exception as ex:  # pragma: no cover
-            e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+            del m
+            return world * steps * STEP_FRAMES / float(tm.item()), int(res["d2h_bytes"])
 
+        try:
+            es = max(3, args.steps // 5)
+            v, d2h = run_e2e("copy", es)
+            e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2), "d2h_bytes_per_step": d2h, "steps": es,
+                   "api": "DenseTSDF.recast_depth_to_map per frame; page-locked host uint16 frames, DEFAULT frame mode: every frame is "
+                          "copied and the copy awaited inside the call (the caller may reuse its buffer at once, as with the reference)"}
+            es2 = max(3, args.steps // 10)
+            vb, _ = run_e2e("borrow", es2)
+            vp, _ = run_e2e("pageable", es2)
+            e2e_modes = {"borrowed_pinned_frames": {"value": vb, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
+                                                    "note": "opt-in set_frame_borrowing(True): no copy, the GPU reads the sampled rows from host "
+                                                            "memory; frames must stay untouched until the next flush"},
+                         "pageable_frames": {"value": vp, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
+                                             "note": "what np.frombuffer(depth_msg.data) gives the ROS node (taichislam_node.py:381-382)"}}
+        except Exception as ex:  # pragma: no cover
+            e2e = e2e or {"value": None, "unit": UNIT, "error": repr(ex)}
+            e2e_modes["error"] = repr(ex)
+
+    c5 = None
+    if world > 1 and not args.no_c5:
+        try:
+            c5 = c5_extras(rank, local_rank, world, dist, torch)
+        except Exception as ex:  # pragma: no cover
+            c5 = {"error": repr(ex)}
+
+    cfg = dict(CONFIG)
+    cfg.update({"parallelism": f"submap-sharded x{world} (no data-path collective in the frame metric; the tiled global-map "
+                               f"exchange is measured in extras.c5 for N > 1)",
+                "l2": f"inputs cycle through {POOL_BATCHES} batches = {POOL_BATCHES * BATCH * syn.H * syn.W * 2 / 1e6:.0f} MB > 126 MB L2"})
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: synthetic 640x480 uint16 depth stream (S2: camera-centred sphere R=4 m, circle poses) "
-                               "-> 512^3 TSDF, voxel 0.05 m, recast_step 2, max_ray 10 m; marching cubes of the result "
-                               "reported in extras (per-output, not per-frame)",
-                   "frames_per_step": BATCH, "grid": "512^3", "parallelism": f"submap-sharded x{world} (no data-path collective)",
-                   "l2": f"inputs cycle through {POOL_BATCHES} batches = {POOL_BATCHES * BATCH * syn.H * syn.W * 2 / 1e6:.0f} MB > 126 MB L2"},
-        "roofline": {"bound": "hbm", "kernel": "k_raymarch", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "config": cfg,
+        "roofline": {"bound": "hbm", "kernel": "process_new_pcl = k_ray_setup + k_seg_walk/class/scan/place + k_march_blocks (dominant)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     "traffic": (load_traffic("k_raymarch") or (None, None))[0], "traffic_source": (load_traffic("k_raymarch") or (None, None))[1],
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": {"bucket": bucket_ms, "raymarch": ray_ms, "commit": commit_ms},
+                     "traffic": tr[0], "traffic_source": tr[1], "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_launch,
+                     "kernel_ms": {"bucket": bucket_ms, "raymarch": ray_ms, "commit": commit_ms, "ray_setup": float(km[3]),
+                                   "seg_walk_class_scan": float(km[4]), "seg_place": float(km[5]), "march_blocks": march_only},
+                     "dominant_kernel_alone": {"kernel": "k_march_blocks", "ms": march_only,
+                                               "frac": (bytes_launch / (march_only * 1e-3) / 1e9 / peak) if march_only == march_only and march_only > 0 else None},
                      "algorithmic_bytes_per_frame_all_kernels": frame_bytes},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "extras": {"marching_cubes": mc, "per_frame": {"rays": st["n_rays"] / max(args.steps * BATCH, 1),
-                                                         "voxel_updates": st["n_updates"] / max(args.steps * BATCH, 1)},
-                   "voxel_blocks": st["n_blocks"]},
+        "extras": {"marching_cubes": mc, "per_frame": {"rays": st["n_rays"] / max(n_l * BATCH, 1),
+                                                         "voxel_updates": st["n_updates"] / max(n_l * BATCH, 1)},
+                   "voxel_blocks": st["n_blocks"], "march": {k: v / n_l for k, v in mstats.items()}, "e2e_modes": e2e_modes, "c5": c5},
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:

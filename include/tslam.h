@@ -207,6 +207,13 @@ int tslam_tsdf_fuse_pending(tslam_tsdf_t* dst, tslam_tsdf_t* src, void* stream);
 int tslam_tsdf_commit_fused(tslam_tsdf_t* m, void* stream);
 /* Owner rank of block (bx,by,bz). */
 int tslam_tiling_owner(tslam_tsdf_t* m, const int32_t* tiles3, int32_t world, int32_t bx, int32_t by, int32_t bz, int32_t* owner);
+/* Tile boundaries.  By default the volume is cut into equal slices; tslam_tiling_set_cuts installs block-coordinate
+ * cuts per axis (cuts_a[k] .. cuts_a[k+1]-1 = tile k, tiles3[a]+1 strictly increasing values; NULL tiles3 = back to
+ * the default) - the host layer derives them from the occupied blocks (tslam_tsdf_dirty_hist: HOST int32[3][1024],
+ * histogram of the block coordinates + 512 of the blocks touched since the last commit, per axis) so that a flat
+ * flight volume does not leave half the ranks without surface.  Every rank must install the same cuts. */
+int tslam_tiling_set_cuts(tslam_tsdf_t* m, const int32_t* tiles3, const int32_t* cuts_x, const int32_t* cuts_y, const int32_t* cuts_z);
+int tslam_tsdf_dirty_hist(tslam_tsdf_t* m, int32_t* hist3x1024, void* stream);
 /* counts_out[world] (HOST): touched blocks owned by every other rank.  Synchronises. */
 int tslam_tsdf_foreign_count(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, int32_t* counts_out, void* stream);
 /* Pack those blocks grouped by destination rank and clear them locally: keys int64[cap], acc f32[cap,4096,2]
@@ -222,6 +229,17 @@ int tslam_tsdf_halo_pack(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, i
                          int64_t* keys, float* tw, uint8_t* obs, void* stream);
 /* Insert received halo blocks as GHOSTS: read by marching cubes, never counted / exported / meshed as owners. */
 int tslam_tsdf_ghost_unpack(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* tw, const uint8_t* obs, void* stream);
+/* Textured maps (colour is fused with the geometry, dense_tsdf.py:276-277): the same four calls with the colour
+ * plane f32[cap,4096,4] riding along (pending sum of w*colour for the fusion exchange, committed colour for the halo).
+ * col must be given for a textured map and NULL for an untextured one. */
+int tslam_tsdf_foreign_pack2(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
+                             int64_t cap, int64_t* keys, float* acc, uint8_t* obs, int8_t* occ, float* col, void* stream);
+int tslam_tsdf_unpack_add2(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* acc, const uint8_t* obs, const int8_t* occ,
+                           const float* col, void* stream);
+int tslam_tsdf_halo_pack2(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts, int64_t cap,
+                          int64_t* keys, float* tw, uint8_t* obs, float* col, void* stream);
+int tslam_tsdf_ghost_unpack2(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* tw, const uint8_t* obs, const float* col,
+                             void* stream);
 
 /* ----------------------------------------------------------------------------
  * Marching cubes  (MarchingCubeMesher, marching_cube_mesher.py)

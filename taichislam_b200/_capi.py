@@ -92,12 +92,18 @@ SIGNATURES = {
     "tslam_tsdf_fuse_pending": (C.c_int, [_vp, _vp, _vp]),
     "tslam_tsdf_commit_fused": (C.c_int, [_vp, _vp]),
     "tslam_tiling_owner": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_i32)]),
+    "tslam_tiling_set_cuts": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "tslam_tsdf_dirty_hist": (C.c_int, [_vp, _vp, _vp]),
     "tslam_tsdf_foreign_count": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "tslam_tsdf_foreign_pack": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tslam_tsdf_unpack_add": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tslam_tsdf_halo_count": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "tslam_tsdf_halo_pack": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tslam_tsdf_ghost_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "tslam_tsdf_foreign_pack2": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tslam_tsdf_unpack_add2": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tslam_tsdf_halo_pack2": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tslam_tsdf_ghost_unpack2": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tslam_mc_generate": (C.c_int, [_vp, _i32, _f32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),
     "tslam_esdf_update": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp]),
     "tslam_esdf_gather": (C.c_int, [_vp, _i32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),

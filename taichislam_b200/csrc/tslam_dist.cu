@@ -12,36 +12,55 @@
 #include <cstring>
 #include "tslam_internal.cuh"
 
+#define TS_MAX_TILES_AXIS 16
 struct TsTiling {
   int tiles[3];
   int rank, world;
-  int bmin[3];   // first block coordinate of the volume per axis
-  int ext[3];    // tile extent in blocks per axis
+  int cuts[3][TS_MAX_TILES_AXIS + 1];  // tile k of axis a owns block coordinates [cuts[a][k], cuts[a][k+1])
 };
 
-__device__ __forceinline__ int tile_coord(const TsTiling& t, int axis, int b) {
-  int c = (b - t.bmin[axis]) / t.ext[axis];
-  return c < 0 ? 0 : (c >= t.tiles[axis] ? t.tiles[axis] - 1 : c);
+__host__ __device__ __forceinline__ int tile_coord(const TsTiling& t, int axis, int b) {
+  int c = 0;
+  while (c + 1 < t.tiles[axis] && b >= t.cuts[axis][c + 1]) ++c;  // (blocks outside the cut range belong to the end tiles)
+  return c;
 }
-__device__ __forceinline__ int tile_owner(const TsTiling& t, int bx, int by, int bz) {
+__host__ __device__ __forceinline__ int tile_owner(const TsTiling& t, int bx, int by, int bz) {
   return (tile_coord(t, 0, bx) * t.tiles[1] + tile_coord(t, 1, by)) * t.tiles[2] + tile_coord(t, 2, bz);
 }
 
+// Tile boundaries: the cuts set by tslam_tiling_set_cuts when they match `tiles3` (data-driven: the host layer puts
+// them at the quantiles of the occupied blocks' marginal histograms, so a flat flight volume does not leave half the
+// ranks empty), else equal slices of the volume.
 static int fill_tiling(tslam_tsdf* m, const int32_t* tiles3, int rank, int world, TsTiling* t) {
-  if (!tiles3 || tiles3[0] < 1 || tiles3[1] < 1 || tiles3[2] < 1 || tiles3[0] * tiles3[1] * tiles3[2] != world || rank < 0 || rank >= world) {
+  if (!tiles3 || tiles3[0] < 1 || tiles3[1] < 1 || tiles3[2] < 1 || tiles3[0] * tiles3[1] * tiles3[2] != world || rank < 0 || rank >= world ||
+      tiles3[0] > TS_MAX_TILES_AXIS || tiles3[1] > TS_MAX_TILES_AXIS || tiles3[2] > TS_MAX_TILES_AXIS) {
     ts_set_error("bad tiling: %d x %d x %d tiles for world size %d", tiles3 ? tiles3[0] : -1, tiles3 ? tiles3[1] : -1, tiles3 ? tiles3[2] : -1, world);
     return TSLAM_E_INVALID;
   }
   const int n[3] = {m->g.N, m->g.N, m->g.Nz}, h[3] = {m->g.hN, m->g.hN, m->g.hNz};
+  const bool custom = m->tile_cuts_set && m->tile_cuts_tiles[0] == tiles3[0] && m->tile_cuts_tiles[1] == tiles3[1] && m->tile_cuts_tiles[2] == tiles3[2];
   for (int a = 0; a < 3; a++) {
     t->tiles[a] = tiles3[a];
     const int lo = (-h[a]) >> TS_BSHIFT, hi = (n[a] - h[a] - 1) >> TS_BSHIFT;  // block range of the volume
-    t->bmin[a] = lo;
-    t->ext[a] = (hi - lo + 1 + tiles3[a] - 1) / tiles3[a];
+    const int ext = (hi - lo + 1 + tiles3[a] - 1) / tiles3[a];
+    for (int k = 0; k <= tiles3[a]; k++) t->cuts[a][k] = custom ? m->tile_cuts[a][k] : lo + k * ext;
   }
   t->rank = rank;
   t->world = world;
   return TSLAM_OK;
+}
+
+// per-axis histograms of the block coordinates of the dirty blocks (coordinate + 512 in [0, 1024))
+__global__ void __launch_bounds__(256) k_dirty_hist(TsGrid g, int* hist) {
+  const int nb = min(*g.n_blocks, g.max_blocks);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    if (!g.dirty_flag[b]) continue;
+    int s, bx, by, bz;
+    ts_unpack_key(g.block_key[b], s, bx, by, bz);
+    atomicAdd(&hist[(bx + 512) & 1023], 1);
+    atomicAdd(&hist[1024 + ((by + 512) & 1023)], 1);
+    atomicAdd(&hist[2048 + ((bz + 512) & 1023)], 1);
+  }
 }
 
 // ---- fusion exchange -------------------------------------------------------------------------------------------
@@ -59,7 +78,7 @@ __global__ void __launch_bounds__(256) k_foreign_count(TsGrid g, TsTiling t, int
 
 // one CTA per block of the pool; foreign dirty blocks copy their planes into the slot group of their owner
 __global__ void __launch_bounds__(256) k_foreign_pack(TsGrid g, TsTiling t, const int* offsets, int* cursor, long long cap,
-                                                       long long* keys, float2* acc_out, uint8_t* obs_out, int8_t* occ_out) {
+                                                       long long* keys, float2* acc_out, uint8_t* obs_out, int8_t* occ_out, float4* col_out) {
   __shared__ long long s_slot;
   const int nb = min(*g.n_blocks, g.max_blocks);
   for (int b = blockIdx.x; b < nb; b += gridDim.x) {
@@ -82,16 +101,18 @@ __global__ void __launch_bounds__(256) k_foreign_pack(TsGrid g, TsTiling t, cons
         acc_out[slot * TS_B3 + v] = g.acc[base + v];
         obs_out[slot * TS_B3 + v] = g.obs[base + v];
         occ_out[slot * TS_B3 + v] = g.occ[base + v];
+        if (col_out) col_out[slot * TS_B3 + v] = g.col[base + v];  // textured maps: pending sum of w * colour (dense_tsdf.py:277)
       }
       g.acc[base + v] = make_float2(0.f, 0.f);  // the block stays allocated but empty on this rank
       g.obs[base + v] = 0;
       g.occ[base + v] = 0;
+      if (col_out) g.col[base + v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }
 
 __global__ void __launch_bounds__(256) k_unpack_add(TsGrid g, long long n, const long long* keys, const float2* acc_in,
-                                                     const uint8_t* obs_in, const int8_t* occ_in) {
+                                                     const uint8_t* obs_in, const int8_t* occ_in, const float4* col_in) {
   __shared__ int s_blk;
   for (long long q = blockIdx.x; q < n; q += gridDim.x) {
     __syncthreads();
@@ -108,6 +129,13 @@ __global__ void __launch_bounds__(256) k_unpack_add(TsGrid g, long long n, const
       const uint8_t o = obs_in[q * TS_B3 + v];
       const int oc = occ_in[q * TS_B3 + v];
       if (a.x != 0.f || a.y != 0.f) atomicAdd(&g.acc[base + v], a);  // several ranks may send the same block
+      if (col_in) {
+        const float4 c = col_in[q * TS_B3 + v];
+        if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {
+          float* cp = reinterpret_cast<float*>(&g.col[base + v]);
+          atomicAdd(cp, c.x); atomicAdd(cp + 1, c.y); atomicAdd(cp + 2, c.z);
+        }
+      }
       if (o && g.obs[base + v] == 0) g.obs[base + v] = 2;            // observed, value pending (2 -> 1 at commit)
       if (oc) {
         // blocks with the same key (from different senders) are processed by different CTAs: go through a word CAS
@@ -133,9 +161,8 @@ __device__ __forceinline__ int halo_dests(const TsTiling& t, int bx, int by, int
   int tc[3], lo[3], hi[3];
   for (int a = 0; a < 3; a++) {
     tc[a] = tile_coord(t, a, b[a]);
-    const int first = t.bmin[a] + tc[a] * t.ext[a];
-    lo[a] = (b[a] == first) && tc[a] > 0;
-    hi[a] = (b[a] == first + t.ext[a] - 1) && tc[a] < t.tiles[a] - 1;
+    lo[a] = (b[a] == t.cuts[a][tc[a]]) && tc[a] > 0;
+    hi[a] = (b[a] == t.cuts[a][tc[a] + 1] - 1) && tc[a] < t.tiles[a] - 1;
   }
   int n = 0;
   for (int dx = -1; dx <= 1; dx++)
@@ -163,7 +190,7 @@ __global__ void __launch_bounds__(256) k_halo_count(TsGrid g, TsTiling t, int* c
 }
 
 __global__ void __launch_bounds__(256) k_halo_pack(TsGrid g, TsTiling t, const int* offsets, int* cursor, long long cap, long long* keys,
-                                                    float2* tw_out, uint8_t* obs_out) {
+                                                    float2* tw_out, uint8_t* obs_out, float4* col_out) {
   __shared__ long long s_slot[26];
   __shared__ int s_n;
   const int nb = min(*g.n_blocks, g.max_blocks);
@@ -190,13 +217,14 @@ __global__ void __launch_bounds__(256) k_halo_pack(TsGrid g, TsTiling t, const i
       for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
         tw_out[slot * TS_B3 + v] = g.tw[base + v];
         obs_out[slot * TS_B3 + v] = g.obs[base + v];
+        if (col_out) col_out[slot * TS_B3 + v] = g.col[base + v];
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) k_ghost_unpack(TsGrid g, long long n, const long long* keys, const float2* tw_in,
-                                                       const uint8_t* obs_in) {
+                                                       const uint8_t* obs_in, const float4* col_in) {
   __shared__ int s_blk;
   for (long long q = blockIdx.x; q < n; q += gridDim.x) {
     __syncthreads();
@@ -211,6 +239,7 @@ __global__ void __launch_bounds__(256) k_ghost_unpack(TsGrid g, long long n, con
     for (int v = threadIdx.x; v < TS_B3; v += blockDim.x) {
       g.tw[base + v] = tw_in[q * TS_B3 + v];
       g.obs[base + v] = obs_in[q * TS_B3 + v];
+      if (col_in) g.col[base + v] = col_in[q * TS_B3 + v];
     }
   }
 }
@@ -230,13 +259,36 @@ extern "C" int tslam_tiling_owner(tslam_tsdf_t* m, const int32_t* tiles3, int32_
   TsTiling t;
   int rc = fill_tiling(m, tiles3, 0, world, &t);
   if (rc) return rc;
-  int c[3];
-  const int b[3] = {bx, by, bz};
+  *owner = tile_owner(t, bx, by, bz);
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tiling_set_cuts(tslam_tsdf_t* m, const int32_t* tiles3, const int32_t* cuts_x, const int32_t* cuts_y, const int32_t* cuts_z) {
+  if (!m) return TSLAM_E_INVALID;
+  if (!tiles3) { m->tile_cuts_set = 0; return TSLAM_OK; }  // back to equal slices of the volume
+  const int32_t* cu[3] = {cuts_x, cuts_y, cuts_z};
   for (int a = 0; a < 3; a++) {
-    c[a] = (b[a] - t.bmin[a]) / t.ext[a];
-    c[a] = c[a] < 0 ? 0 : (c[a] >= t.tiles[a] ? t.tiles[a] - 1 : c[a]);
+    if (tiles3[a] < 1 || tiles3[a] > TS_MAX_TILES_AXIS || !cu[a]) { ts_set_error("bad tile cuts"); return TSLAM_E_INVALID; }
+    for (int k = 0; k < tiles3[a]; k++)
+      if (cu[a][k] >= cu[a][k + 1]) { ts_set_error("tile cuts must increase strictly (axis %d)", a); return TSLAM_E_INVALID; }
   }
-  *owner = (c[0] * t.tiles[1] + c[1]) * t.tiles[2] + c[2];
+  for (int a = 0; a < 3; a++) {
+    m->tile_cuts_tiles[a] = tiles3[a];
+    for (int k = 0; k <= tiles3[a]; k++) m->tile_cuts[a][k] = cu[a][k];
+  }
+  m->tile_cuts_set = 1;
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_dirty_hist(tslam_tsdf_t* m, int32_t* hist3x1024, void* stream) {
+  if (!m || !hist3x1024) return TSLAM_E_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!m->tile_hist) TS_CUDA(cudaMalloc(&m->tile_hist, 3 * 1024 * sizeof(int)));
+  TS_CUDA(cudaMemsetAsync(m->tile_hist, 0, 3 * 1024 * sizeof(int), st));
+  k_dirty_hist<<<m->sm_count * 2, 256, 0, st>>>(m->g, m->tile_hist);
+  TS_LAUNCH_CHECK(m);
+  TS_CUDA(cudaMemcpyAsync(hist3x1024, m->tile_hist, 3 * 1024 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TS_CUDA(cudaStreamSynchronize(st));
   return TSLAM_OK;
 }
 
@@ -262,7 +314,13 @@ extern "C" int tslam_tsdf_foreign_count(tslam_tsdf_t* m, const int32_t* tiles3, 
 // keys int64[cap], acc f32[cap,4096,2], obs u8[cap,4096], occ i8[cap,4096] (DEVICE).
 extern "C" int tslam_tsdf_foreign_pack(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
                                        int64_t cap, int64_t* keys, float* acc, uint8_t* obs, int8_t* occ, void* stream) {
+  return tslam_tsdf_foreign_pack2(m, tiles3, rank, world, counts, cap, keys, acc, obs, occ, nullptr, stream);
+}
+extern "C" int tslam_tsdf_foreign_pack2(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
+                                        int64_t cap, int64_t* keys, float* acc, uint8_t* obs, int8_t* occ, float* col, void* stream) {
   if (!m || !counts || world > 24) return TSLAM_E_INVALID;
+  if (col && !m->g.col) { ts_set_error("colour plane requested from an untextured map"); return TSLAM_E_INVALID; }
+  if (!col && m->g.col) { ts_set_error("textured map: the colour plane must travel with the blocks (pass col)"); return TSLAM_E_INVALID; }
   TsTiling t;
   int rc = fill_tiling(m, tiles3, rank, world, &t);
   if (rc) return rc;
@@ -273,7 +331,7 @@ extern "C" int tslam_tsdf_foreign_pack(tslam_tsdf_t* m, const int32_t* tiles3, i
   int* d_cur = m->scratch_i + 40;
   TS_CUDA(cudaMemcpyAsync(d_off, h_off, world * sizeof(int), cudaMemcpyHostToDevice, st));
   TS_CUDA(cudaMemsetAsync(d_cur, 0, 24 * sizeof(int), st));
-  k_foreign_pack<<<m->sm_count * 4, 256, 0, st>>>(m->g, t, d_off, d_cur, cap, (long long*)keys, (float2*)acc, obs, occ);
+  k_foreign_pack<<<m->sm_count * 4, 256, 0, st>>>(m->g, t, d_off, d_cur, cap, (long long*)keys, (float2*)acc, obs, occ, (float4*)col);
   TS_LAUNCH_CHECK(m);
   TS_CUDA(cudaStreamSynchronize(st));  // h_off is on the stack
   return TSLAM_OK;
@@ -281,10 +339,15 @@ extern "C" int tslam_tsdf_foreign_pack(tslam_tsdf_t* m, const int32_t* tiles3, i
 
 extern "C" int tslam_tsdf_unpack_add(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* acc, const uint8_t* obs,
                                      const int8_t* occ, void* stream) {
+  return tslam_tsdf_unpack_add2(m, n, keys, acc, obs, occ, nullptr, stream);
+}
+extern "C" int tslam_tsdf_unpack_add2(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* acc, const uint8_t* obs,
+                                      const int8_t* occ, const float* col, void* stream) {
   if (!m || n < 0) return TSLAM_E_INVALID;
+  if (col && !m->g.col) { ts_set_error("colour plane given to an untextured map"); return TSLAM_E_INVALID; }
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  k_unpack_add<<<(int)(n < m->sm_count * 4 ? n : m->sm_count * 4), 256, 0, st>>>(m->g, n, (const long long*)keys, (const float2*)acc, obs, occ);
+  k_unpack_add<<<(int)(n < m->sm_count * 4 ? n : m->sm_count * 4), 256, 0, st>>>(m->g, n, (const long long*)keys, (const float2*)acc, obs, occ, (const float4*)col);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }
@@ -309,7 +372,12 @@ extern "C" int tslam_tsdf_halo_count(tslam_tsdf_t* m, const int32_t* tiles3, int
 
 extern "C" int tslam_tsdf_halo_pack(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
                                     int64_t cap, int64_t* keys, float* tw, uint8_t* obs, void* stream) {
+  return tslam_tsdf_halo_pack2(m, tiles3, rank, world, counts, cap, keys, tw, obs, nullptr, stream);
+}
+extern "C" int tslam_tsdf_halo_pack2(tslam_tsdf_t* m, const int32_t* tiles3, int32_t rank, int32_t world, const int32_t* counts,
+                                     int64_t cap, int64_t* keys, float* tw, uint8_t* obs, float* col, void* stream) {
   if (!m || !counts || world > 24) return TSLAM_E_INVALID;
+  if (col && !m->g.col) { ts_set_error("colour plane requested from an untextured map"); return TSLAM_E_INVALID; }
   TsTiling t;
   int rc = fill_tiling(m, tiles3, rank, world, &t);
   if (rc) return rc;
@@ -320,17 +388,22 @@ extern "C" int tslam_tsdf_halo_pack(tslam_tsdf_t* m, const int32_t* tiles3, int3
   int* d_cur = m->scratch_i + 40;
   TS_CUDA(cudaMemcpyAsync(d_off, h_off, world * sizeof(int), cudaMemcpyHostToDevice, st));
   TS_CUDA(cudaMemsetAsync(d_cur, 0, 24 * sizeof(int), st));
-  k_halo_pack<<<m->sm_count * 4, 256, 0, st>>>(m->g, t, d_off, d_cur, cap, (long long*)keys, (float2*)tw, obs);
+  k_halo_pack<<<m->sm_count * 4, 256, 0, st>>>(m->g, t, d_off, d_cur, cap, (long long*)keys, (float2*)tw, obs, (float4*)col);
   TS_LAUNCH_CHECK(m);
   TS_CUDA(cudaStreamSynchronize(st));
   return TSLAM_OK;
 }
 
 extern "C" int tslam_tsdf_ghost_unpack(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* tw, const uint8_t* obs, void* stream) {
+  return tslam_tsdf_ghost_unpack2(m, n, keys, tw, obs, nullptr, stream);
+}
+extern "C" int tslam_tsdf_ghost_unpack2(tslam_tsdf_t* m, int64_t n, const int64_t* keys, const float* tw, const uint8_t* obs, const float* col,
+                                        void* stream) {
   if (!m || n < 0) return TSLAM_E_INVALID;
+  if (col && !m->g.col) { ts_set_error("colour plane given to an untextured map"); return TSLAM_E_INVALID; }
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  k_ghost_unpack<<<(int)(n < m->sm_count * 4 ? n : m->sm_count * 4), 256, 0, st>>>(m->g, n, (const long long*)keys, (const float2*)tw, obs);
+  k_ghost_unpack<<<(int)(n < m->sm_count * 4 ? n : m->sm_count * 4), 256, 0, st>>>(m->g, n, (const long long*)keys, (const float2*)tw, obs, (const float4*)col);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }

@@ -357,6 +357,8 @@ struct tslam_tsdf {
   cudaEvent_t* ev;          // profiling ring: TS_PROF_RING launches x 4 events (created lazily)
   long long prof_launches;  // integrate launches recorded since profiling was switched on
   int sm_count;
+  int tile_cuts_set, tile_cuts_tiles[3], tile_cuts[3][17];  // data-driven tile boundaries of a tiled global map (tslam_dist.cu)
+  int* tile_hist;      // device scratch of tslam_tsdf_dirty_hist (allocated on first use)
   TsMarchWs mw;        // block-binned ray march workspace (tslam_march.cu)
   int march_mode;      // 0 = legacy k_raymarch, 1 = block-binned (default for untextured maps), env TSLAM_MARCH
   int march_verify;    // TSLAM_MARCH_VERIFY=1: every fast-path index is re-computed exactly, mismatches counted

@@ -758,6 +758,7 @@ void ts_march_free(tslam_tsdf* m) {
 
 // ray set-up of the rays listed since the last call (one frame group; g0 = its first frame)
 int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, int g0) {
+  if (!m->mw.rays) { int rca = ts_march_alloc(m); if (rca) return rca; }
   k_ray_setup<<<m->sm_count * 16, 256, 0, st>>>(batch, m->in, m->g, m->buckets, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters,
                                                 (uint32_t)g0);
   TS_LAUNCH_CHECK(m);

@@ -812,7 +812,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     m->march_verify = getenv("TSLAM_MARCH_VERIFY") != nullptr;
     m->frame_group = TSLAM_MAX_BATCH;  // one round per launch (rounds of 4/8/16 frames were measured: no gain, see profiles/r02_march.md)
     if (const char* fg = getenv("TSLAM_FRAME_GROUP")) { const int v = atoi(fg); if (v >= 1 && v <= TSLAM_MAX_BATCH) m->frame_group = v; }
-    if (m->march_mode) { int rcm = ts_march_alloc(m); if (rcm) return rcm; }
+    // (the march workspace - ~2 GB for 640x480 frames - is allocated by the first integrate launch: global maps that are
+    // only ever fused into never pay for it)
   }
   TS_CUDA(cudaFuncSetAttribute(k_raymarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM));
   TS_CUDA(cudaFuncSetAttribute(k_raymarch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_TEX));
@@ -830,6 +831,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (g.esdf) cudaFree(g.esdf);
   if (m->esdf_aux) cudaFree(m->esdf_aux);
   if (m->mc_scratch) cudaFree(m->mc_scratch);
+  if (m->tile_hist) cudaFree(m->tile_hist);
   if (g.cword) cudaFree(g.cword);
   if (g.col) cudaFree(g.col);
   if (m->tex_stage) cudaFree(m->tex_stage);
@@ -838,7 +840,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
-  if (m->march_mode) ts_march_free(m);
+  if (m->mw.rays) ts_march_free(m);
   cudaFree(m->counters); cudaFree(m->pose_R); cudaFree(m->pose_T); cudaFree(m->colormap);
   if (m->ev) { for (int i = 0; i < TS_PROF_EV * TS_PROF_RING; i++) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
   delete m;
@@ -1051,10 +1053,10 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
         k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap,
                                               m->ray_list, m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw, g0);
         TS_LAUNCH_CHECK(m);
+        if (pe && g0 + ng >= nf) TS_CUDA(cudaEventRecord(pe[1], st));  // (one round: pe[1]..pe[4] is the ray set-up)
         int rcs = ts_march_setup(m, st, batch, bshift, g0);
         if (rcs) return rcs;
       }
-      if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
       int rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
       if (rcm) return rcm;
     } else {

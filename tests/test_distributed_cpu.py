@@ -96,3 +96,21 @@ def test_gloo_world2_exchange_and_gather():
     for p in ps:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_balanced_tiling_follows_the_data():
+    """Flat flight volume: all blocks within 3 z-layers.  Equal slices (2x2x2) would leave 4 of 8 tiles empty; the
+    data-driven tiling puts no cut through empty space and balances the marginals."""
+    from taichislam_b200.distributed import balanced_tiling
+    hist = np.zeros((3, 1024), np.int64)
+    hist[0, 512 - 40:512 + 40] = 100
+    hist[1, 512 - 30:512 + 50] = 100
+    hist[2, 512 - 1:512 + 2] = [2000, 4000, 2000]
+    tiles, cuts = balanced_tiling(hist, 8)
+    assert tiles[0] * tiles[1] * tiles[2] == 8 and tiles[2] <= 2
+    for a in range(3):
+        c = np.asarray(cuts[a]) + 512
+        shares = [hist[a][c[i]:c[i + 1]].sum() / hist[a].sum() for i in range(tiles[a])]
+        assert len(c) == tiles[a] + 1 and np.all(np.diff(c) > 0) and abs(sum(shares) - 1) < 1e-9
+        assert max(shares) <= 1.0 / tiles[a] + 0.26   # (a 3-layer axis cannot be cut finer than its layers)
+    assert balanced_tiling(np.zeros((3, 1024)), 4)[1] is None

@@ -311,7 +311,12 @@ def test_binned_march_overflow_and_legacy_paths_agree(monkeypatch):
     compare_voxels(ref, o.gather(), TOL)
     g1, _ = _march_run(monkeypatch, {"TSLAM_SEG_CAP": "20000"})
     assert g1.march_stats()["n_generic"] > 0
-    compare_voxels(g1.gather(), ref, TOL)
+    # here EVERY sample went through the fallback (plain f32 global reductions, arbitrary order): the handful of voxels at
+    # the sensor origin sum ~1e5 samples each and carry the f32 accumulation noise (<= 1e-4 relative) that the
+    # shared-memory fixed-point sums of the binned path do not have
+    compare_voxels(g1.gather(), ref, 2e-3)
+    a, b = as_dict_rows(*g1.gather()), as_dict_rows(*ref)
+    assert (np.abs(a[1] - b[1]) > TOL).mean() < 1e-4
     monkeypatch.delenv("TSLAM_SEG_CAP")
     g2, _ = _march_run(monkeypatch, {"TSLAM_MARCH": "legacy"})
     assert g2.march_stats()["n_segs"] == 0

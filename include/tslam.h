@@ -260,6 +260,12 @@ int tslam_mc_generate2(tslam_tsdf_t* m, int32_t step, float tsdf_surface_thres, 
 /* Converged 26-neighbour signed distance wavefront over the observed voxels of
  * `submap`.  *n_sweeps_out (host, optional) = global sweeps until no change. */
 int tslam_esdf_update(tslam_tsdf_t* m, int32_t submap, int32_t* n_sweeps_out, void* stream);
+/* Same with control and statistics.  mode 0: INCREMENTAL when the kept state allows it (same submap as the previous
+ * update, no reset / load_numpy / ghost import since) - only the voxels that changed since the last update, the voxels
+ * whose value may have been derived from them (raise wave) and whatever those lower again are recomputed; the result
+ * is bit-identical to a full recompute.  mode 1: full recompute.  stats4 (HOST, may be NULL): lower sweeps,
+ * raise sweeps (-1 = the update was full), changed voxels, suspect voxels.  Synchronises. */
+int tslam_esdf_update2(tslam_tsdf_t* m, int32_t submap, int32_t mode, int32_t* stats4, void* stream);
 /* ESDF of observed voxels: idx int32[cap,3], esdf f32[cap] (DEVICE). Synchronises. */
 int tslam_esdf_gather(tslam_tsdf_t* m, int32_t submap, int64_t cap, int32_t* idx, float* esdf, int64_t* n_out,
                       void* stream);

@@ -106,6 +106,7 @@ SIGNATURES = {
     "tslam_tsdf_ghost_unpack2": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "tslam_mc_generate": (C.c_int, [_vp, _i32, _f32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),
     "tslam_esdf_update": (C.c_int, [_vp, _i32, C.POINTER(_i32), _vp]),
+    "tslam_esdf_update2": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "tslam_esdf_gather": (C.c_int, [_vp, _i32, _i64, _vp, _vp, C.POINTER(_i64), _vp]),
     "tslam_octo_create": (C.c_int, [C.POINTER(OctoConfig), C.POINTER(_vp)]),
     "tslam_octo_destroy": (C.c_int, [_vp]),

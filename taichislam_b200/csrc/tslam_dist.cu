@@ -403,6 +403,7 @@ extern "C" int tslam_tsdf_ghost_unpack2(tslam_tsdf_t* m, int64_t n, const int64_
   if (col && !m->g.col) { ts_set_error("colour plane given to an untextured map"); return TSLAM_E_INVALID; }
   if (n == 0) return TSLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  m->esdf_full_needed = 1;
   k_ghost_unpack<<<(int)(n < m->sm_count * 4 ? n : m->sm_count * 4), 256, 0, st>>>(m->g, n, (const long long*)keys, (const float2*)tw, obs, (const float4*)col);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;

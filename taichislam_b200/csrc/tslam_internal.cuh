@@ -49,6 +49,7 @@ struct TsGrid {
   float4* col;                // [max_blocks*4096] texture: committed colour rgb (+pad)
   uint8_t* ghost;             // [max_blocks] 1 = halo copy of a block owned by another rank (multi-GPU tiling)
   float* esdf;                // [max_blocks*4096] (allocated lazily by the ESDF path)
+  int* esdf_dirty;            // [max_blocks] block committed since the last ESDF update (seeds the incremental wave)
   int* dirty_flag;            // [max_blocks]
   int* dirty_list;            // [max_blocks]
   int* n_dirty;
@@ -349,7 +350,8 @@ struct tslam_tsdf {
   float* pose_T;       // [max_submaps*3]
   float* colormap;     // device jet LUT [1024*3]
   int* scratch_i;      // small device scratch (counters for gather etc.)
-  void* esdf_aux;      // ESDF: neighbour table, epochs, per-sweep change flags (allocated with g.esdf)
+  void* esdf_aux;      // ESDF: neighbour table, epochs, per-sweep change flags, class bytes (allocated with g.esdf)
+  int esdf_full_needed, esdf_submap;  // the next update recomputes everything (first use, reset, bulk load) / submap of the kept state
   void* mc_scratch;    // marching cubes: per-block triangle counts / offsets (allocated on first use)
   long long launches;
   int n_integrate_calls;

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) k_commit(TsGrid g, int clamp, int fused_o
         }
       }
     }
-    if (threadIdx.x == 0) g.dirty_flag[blk] = 0;
+    if (threadIdx.x == 0) { g.dirty_flag[blk] = 0; g.esdf_dirty[blk] = 1; }
   }
 }
 // ---------------------------------------------------------------------------
@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(256) k_commit_tma(TsGrid g, int clamp, int fus
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be overwritten by the next block's loads
       g.dirty_flag[blk] = 0;
+      g.esdf_dirty[blk] = 1;
     }
     __syncthreads();
   }
@@ -731,6 +732,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   TS_CUDA(cudaMalloc(&g.dirty_flag, (size_t)g.max_blocks * 4));
   TS_CUDA(cudaMalloc(&g.dirty_list, (size_t)g.max_blocks * 4));
   TS_CUDA(cudaMemset(g.dirty_flag, 0, (size_t)g.max_blocks * 4));
+  TS_CUDA(cudaMalloc(&g.esdf_dirty, (size_t)g.max_blocks * 4));
+  TS_CUDA(cudaMemset(g.esdf_dirty, 0, (size_t)g.max_blocks * 4));
   TS_CUDA(cudaMalloc(&m->scratch_i, 64 * sizeof(int)));
   TS_CUDA(cudaMemset(m->scratch_i, 0, 64 * sizeof(int)));
   g.n_blocks = m->scratch_i + 0;
@@ -836,7 +839,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (g.col) cudaFree(g.col);
   if (m->tex_stage) cudaFree(m->tex_stage);
   if (m->rgb_stage) cudaFree(m->rgb_stage);
-  cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
+  cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.esdf_dirty); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
@@ -853,6 +856,7 @@ extern "C" int tslam_tsdf_reset(tslam_tsdf_t* m, void* stream) {
   TsGrid& g = m->g;
   int nb = 0;
   m->n_integrate_calls = 0;  // pending sums are discarded with the blocks
+  m->esdf_full_needed = 1;   // ... and the ESDF state
   m->q_n = 0;                // ... and so are queued frames
   m->q_gathered = 0;
   TS_CUDA(cudaMemcpyAsync(&nb, g.n_blocks, 4, cudaMemcpyDeviceToHost, st));
@@ -1463,6 +1467,7 @@ extern "C" int tslam_tsdf_scatter2(tslam_tsdf_t* m, int32_t submap, int64_t n, c
   if (rc) return rc;
   int grid = (int)((n + 255) / 256);
   if (grid > m->sm_count * 32) grid = m->sm_count * 32;
+  m->esdf_full_needed = 1;  // bulk load: values change without a commit
   k_scatter<<<grid, 256, 0, st>>>(m->g, submap, n, idx, tsdf, w, occ, color);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;

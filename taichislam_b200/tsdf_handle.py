@@ -274,6 +274,12 @@ class TsdfHandle:
         capi.check(self.L.tslam_esdf_update(self.h, int(submap), C.byref(sw), capi.stream_ptr()))
         return int(sw.value)
 
+    def esdf_update2(self, submap=0, full=False):
+        """-> dict(lower_sweeps, raise_sweeps (-1: full recompute), changed, suspect)."""
+        st = np.zeros(4, np.int32)
+        capi.check(self.L.tslam_esdf_update2(self.h, int(submap), 1 if full else 0, capi.np_ptr(st), capi.stream_ptr()))
+        return dict(lower_sweeps=int(st[0]), raise_sweeps=int(st[1]), changed=int(st[2]), suspect=int(st[3]))
+
     def esdf_gather(self, submap=0):
         torch = self.torch
         cap = self.count_active(submap)

@@ -197,6 +197,44 @@ def test_esdf_matches_dijkstra_oracle():
     assert np.quantile(np.abs(ee - oe1), 0.999) <= 1e-4
 
 
+def test_esdf_incremental_equals_full_512():
+    """BASELINE config 4 at its stated size: 512^3 TSDF + incremental ESDF propagation, an update after every launch
+    of a 20-frame stream whose surface MOVES half way (sphere 3.0 m -> 3.6 m: old fixed-band voxels leave the band,
+    distances grow - the raise wave has to run).  After every update the incrementally maintained field must be
+    bit-identical to a full recompute on a twin map, and at the end to the oracle's multi-source Dijkstra."""
+    from oracle.oracle import OracleTSDF
+    from taichislam_b200.tsdf_handle import TsdfHandle
+    kw = dict(K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    a, b = TsdfHandle(512, 512, **kw), TsdfHandle(512, 512, **kw)
+    Rs, Ts = syn.stream_poses(20, start=40)
+    seen_raise = False
+    for q in range(20):
+        d = syn.scene_sphere(3.0 if q < 10 else 3.6)
+        for g in (a, b):
+            g.integrate_depth(d, Rs[q][None], Ts[q][None])
+        if q % 3 != 2 and q != 19:
+            continue  # an update every third frame: several commits between two updates
+        sa = a.esdf_update2()
+        sb = b.esdf_update2(full=True)
+        assert sb["raise_sweeps"] == -1 and (q == 2 or sa["raise_sweeps"] >= 1)
+        seen_raise |= sa["suspect"] > 0
+        ia, ea = as_dict_rows(*a.esdf_gather())
+        ib, eb = as_dict_rows(*b.esdf_gather())
+        assert np.array_equal(ia, ib)
+        assert np.array_equal(ea, eb), f"frame {q}: max |dESDF| = {np.abs(ea - eb).max()}, {np.sum(ea != eb)} voxels"
+    assert seen_raise
+    # and against the oracle on IDENTICAL TSDF values
+    gi, gt, gw, gocc = a.gather()
+    o = OracleTSDF(map_scale=[25.6, 25.6], K=syn.K_DEPTH, is_global_map=True, max_ray_length=6.0)
+    o.scatter(0, gi, gt, gw, gocc)
+    o.esdf_update()
+    oi, oe = as_dict_rows(*o.esdf_gather())
+    assert np.array_equal(ia, oi) and np.array_equal(ea, oe)
+    # an update with nothing new to do is a no-op
+    s0 = a.esdf_update2()
+    assert s0["changed"] == 0 and s0["suspect"] == 0
+
+
 def test_planner_queries_match_oracle():
     """Batched raycast / is_pos_occupy / is_pos_unobserved / is_near_pos_occupy (mapping_common.py:165-204), bit-exact."""
     from oracle.oracle import OracleTSDF, OracleOctomap

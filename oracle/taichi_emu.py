@@ -168,6 +168,8 @@ class Vec(_Arith):
         self.a = a
 
     def __len__(self): return self.a.shape[0]
+    def __eq__(self, o): return [bool(x) for x in (self.a == (o.a if isinstance(o, Vec) else np.asarray(o))).reshape(-1)]  # elementwise, for all()/any() (dense_esdf.py:268)
+    __hash__ = object.__hash__
     def __iter__(self): return (_wrap(v) for v in self.a) if self.a.ndim == 1 else (Vec(r) for r in self.a)
     def __repr__(self): return f"Vec({self.a!r})"
     def __neg__(self): return Vec(-self.a)

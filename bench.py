@@ -439,6 +439,8 @@ def main():
             m.set_base_pose_submap(0, np.eye(3), np.zeros(3))  # pose-table rows start at zero (mapping_common.py:106-107)
             if mode == "borrow":
                 m.set_frame_borrowing(True)
+            if mode == "commit1":
+                m.set_commit_granularity(1)
             host = host_t.clone() if mode == "pageable" else host_t.pin_memory()
             host_np = host.numpy().view(np.uint16)
             t = t_rank + 51200
@@ -476,9 +478,12 @@ def main():
             es2 = max(3, args.steps // 10)
             vb, _ = run_e2e("borrow", es2)
             vp, _ = run_e2e("pageable", es2)
+            vc, _ = run_e2e("commit1", es2)
             e2e_modes = {"borrowed_pinned_frames": {"value": vb, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
                                                     "note": "opt-in set_frame_borrowing(True): no copy, the GPU reads the sampled rows from host "
                                                             "memory; frames must stay untouched until the next flush"},
+                         "commit_every_frame": {"value": vc, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
+                                                "note": "set_commit_granularity(1): one launch sequence + commit per frame (Wmax clamp granule = frame)"},
                          "pageable_frames": {"value": vp, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
                                              "note": "what np.frombuffer(depth_msg.data) gives the ROS node (taichislam_node.py:381-382)"}}
         except Exception as ex:  # pragma: no cover

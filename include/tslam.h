@@ -106,6 +106,12 @@ int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t 
                            const float* T3, int32_t submap, void* stream);
 int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);
 int tslam_tsdf_set_frame_mode(tslam_tsdf_t* m, int borrow_pinned);
+/* Frames per queue launch, alternating a, b, a, ... (default TSLAM_MAX_BATCH/2 each).  Every launch ends with a commit:
+ * the granule of the Wmax clamp (dense_tsdf.py:267).  (1, 1) = one commit per frame - what a frame-by-frame caller of
+ * the reference sees below Wmax, and the closest a summed update gets to its per-sample clamp at Wmax
+ * (tests/test_oracle_vs_reference_exec.py::test_commit_granularity_vs_per_sample_clamp_at_wmax) - at the price of
+ * one launch sequence per frame. */
+int tslam_tsdf_set_queue_launch(tslam_tsdf_t* m, int32_t frames_a, int32_t frames_b);
 /* Textured maps (texture_enabled).  set_color_camera_intrinsic (mapping_common.py:28-29) + color_same_proj
  * (dense_tsdf.py:16).  The *_tex / *_rgb forms take the colour image uint8 [n_frames,th,tw,3] (channel order as
  * given - DenseTSDF does not swap BGR) or per-point colours uint8 [n,3]; tex == NULL integrates geometry only.

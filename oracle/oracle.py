@@ -41,6 +41,16 @@ class _OctoCfg(C.Structure):
 _lib = None
 
 
+def oracle_colormap():
+    """The oracle's jet LUT [1024,3] (mapping_common.py:158-163)."""
+    out = np.zeros((1024, 3), np.float32)
+    L = lib()
+    L.orc_colormap.argtypes = [C.c_void_p]
+    L.orc_colormap.restype = None
+    L.orc_colormap(_p(out))
+    return out
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -471,6 +471,13 @@ struct Octo {
 // ============================================================================
 extern "C" {
 
+// the jet LUT on its own (tests/test_oracle_cpu.py::test_jet_colormap_golden pins it to tests/golden/jet_1024.json)
+void orc_colormap(float* out3072) {
+  static float cm[1024][3];
+  fill_jet(cm);
+  memcpy(out3072, cm, sizeof(cm));
+}
+
 void* orc_tsdf_create(const TsdfCfg* cfg) {
   Tsdf* m = new Tsdf();
   m->c = *cfg;

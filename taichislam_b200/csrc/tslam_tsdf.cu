@@ -1239,6 +1239,15 @@ static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
   return TSLAM_OK;
 }
 
+extern "C" int tslam_tsdf_set_queue_launch(tslam_tsdf_t* m, int32_t frames_a, int32_t frames_b) {
+  if (!m || frames_a < 1 || frames_a > TSLAM_MAX_BATCH || frames_b < 1 || frames_b > TSLAM_MAX_BATCH) { ts_set_error("queue launch sizes must be in [1, %d]", TSLAM_MAX_BATCH); return TSLAM_E_INVALID; }
+  if (m->q_n > 0) { ts_set_error("frames are queued: flush before changing the launch size"); return TSLAM_E_INVALID; }
+  m->queue_launch[0] = frames_a;
+  m->queue_launch[1] = frames_b;
+  m->q_phase = 0;
+  return TSLAM_OK;
+}
+
 extern "C" int tslam_tsdf_set_frame_mode(tslam_tsdf_t* m, int borrow_pinned) {
   if (!m) return TSLAM_E_INVALID;
   if (m->q_n > 0) { ts_set_error("frames are queued: flush before changing the frame mode"); return TSLAM_E_INVALID; }

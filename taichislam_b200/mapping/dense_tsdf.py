@@ -138,6 +138,12 @@ class DenseTSDF(BaseMap):
         self._flush()
         capi.check(self._h.L.tslam_tsdf_set_frame_mode(self._h.h, int(bool(on))))
 
+    def set_commit_granularity(self, frames):
+        """Frames per internal launch + commit (default 32).  1 = one commit per recast_depth_to_map call: the clamp at
+        Wmax (dense_tsdf.py:267) then sees the same granule as a frame-by-frame run of the reference kernels."""
+        self._flush()
+        capi.check(self._h.L.tslam_tsdf_set_queue_launch(self._h.h, int(frames), int(frames)))
+
     def _stream_ptr(self):
         # raw handle of torch's current stream; the private accessor skips building a Stream object (once per frame)
         if self._raw_stream is not None:

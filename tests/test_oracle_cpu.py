@@ -345,3 +345,13 @@ def test_esdf_literal_matches_executed_reference():
     band = [k for k in keys if abs(t[k]) < gam]
     kept = sum(1 for k in band if m.esdf[k] == t[k])
     assert len(band) > 100 and kept < len(band)   # (here: none of the 298 band voxels survives the three rounds untouched)
+
+
+def test_jet_colormap_golden():
+    """colormap[i] = cm.jet(i/1024) (mapping_common.py:158-163): the oracle's table against tests/golden/jet_1024.json
+    (matplotlib's published algorithm in float64 + three anchor values of the real package, tools/make_golden_jet.py).
+    The export colours of untextured maps (export_color = colormap[int(z-scale)], dense_tsdf.py:360-365) hang on it."""
+    from oracle.oracle import oracle_colormap
+    gold = np.array(json.load(open(os.path.join(HERE, "golden", "jet_1024.json")))["colormap"])
+    cm = oracle_colormap()
+    assert cm.shape == (1024, 3) and np.abs(cm - gold).max() <= 1e-6

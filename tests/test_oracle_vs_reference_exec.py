@@ -285,3 +285,39 @@ def test_f32_state_marching_cubes_and_fusion():
     # sequential weighted mean, thousands of corner splats per voxel in a different (block) order: f32 rounding only
     assert np.abs(gt[kg][fin] - rt[fin]).max() <= 2e-4 and np.percentile(np.abs(gt[kg][fin] - rt[fin]), 99) <= 2e-5
     assert np.all(np.abs(gw[kg][fin] - rw[fin]) <= 1e-4 * np.maximum(1.0, rw[fin]))
+
+
+def test_commit_granularity_vs_per_sample_clamp_at_wmax():
+    """the backend applies the contributions of a commit granule (one frame, or one 32-frame queue
+    launch) as ONE clamped update; the reference clamps per SAMPLE (dense_tsdf.py:264-267).  Below Wmax the two are the same
+    weighted mean; at Wmax the reference's value is an exponential moving average over the last samples in (racy) arrival
+    order.  golden/ref_exec_sat.npz = the reference's kernels executed (f32 state) on 48 frames of a wall 0.5 m from the
+    sensor.  Measured here and stated in DESIGN.md:
+      * voxels that never reach Wmax: every granularity reproduces the reference to 1e-4;
+      * voxels at Wmax (1 % of this map, the cone right in front of the sensor): commits once per frame stay within
+        5.3e-3 m of the reference (median 1e-4), one commit per 32 frames within 1.6e-2 m (median 6e-4) - all are
+        weighted means of the SAME samples, only the averaging window differs, and no schedule of a parallel kernel (the
+        reference's own included) reproduces the serial EMA.  DenseTSDF.set_commit_granularity(1) selects per-frame commits."""
+    from oracle.oracle import OracleTSDF, MODE_CANONICAL
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_sat.npz"))
+    ri, rt, rw = as_dict_rows(g["idx"].astype(np.int32), g["T"], g["W"])
+    out = {}
+    for name, every in (("per_frame", 1), ("per_32", 32)):
+        o = OracleTSDF(map_scale=[6.4, 6.4], K=list(g["K"]), is_global_map=True, max_ray_length=3.0, mode=MODE_CANONICAL)
+        n = len(g["Rs"])
+        for q in range(n):
+            o.integrate_depth(g["Rs"][q], g["Ts"][q], g["depth"], commit=((q + 1) % every == 0 or q == n - 1))
+        oi, ot, ow, _ = as_dict_rows(*o.gather())
+        assert np.array_equal(oi, ri), name
+        out[name] = (ot, ow)
+    sat = rw >= 999.5
+    assert 20 < sat.sum() < 0.05 * len(rw)
+    for name, (ot, ow) in out.items():
+        free = ~sat & (ow < 999.5)
+        assert np.abs(ot[free] - rt[free]).max() <= 1e-4, name          # below the clamp: same value whatever the granule
+        assert np.all(np.abs(ow[free] - rw[free]) <= 1e-4 * np.maximum(1, rw[free]))
+    d1 = np.abs(out["per_frame"][0][sat] - rt[sat])
+    d32 = np.abs(out["per_32"][0][sat] - rt[sat])
+    print(f"saturated voxels {sat.sum()}: per-frame commits max {d1.max():.4f} median {np.median(d1):.4f}; "
+          f"32-frame commits max {d32.max():.4f} median {np.median(d32):.4f}")
+    assert d1.max() <= 0.01 and np.median(d1) <= 5e-4 and d32.max() <= 0.03 and np.median(d32) <= 2e-3   # measured: 0.0053 / 0.0001 and 0.0158 / 0.0006

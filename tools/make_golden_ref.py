@@ -287,6 +287,37 @@ def f32_state():
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
+def saturation():
+    """48 frames of a wall 0.5 m in front of a slowly moving sensor, f32 state: next to the sensor hundreds of rays hit
+    the same voxel per frame and W_TSDF sits at Wmax = 1000 (dense_tsdf.py:267) from the first frame on, where the
+    reference's per-SAMPLE read-modify-write is an exponential moving average over the most recent samples.  The final
+    map goes to tests/golden/ref_exec_sat.npz: tests/test_oracle_vs_reference_exec.py measures how far commits once per
+    frame / once per 32 frames (sum of the contributions, then one clamped update) are from it."""
+    emu.f16.np = np.float32
+    ref = emu.load_reference()
+    from taichislam_b200 import synthetic as syn
+    K = [v / 10 if i in (0, 2, 4, 5) else v for i, v in enumerate(syn.K_DEPTH)]
+    d = np.full((48, 64), 500, np.uint16)
+    d[:, 40:] = 650   # a step in the wall
+    m = ref.dense_tsdf.DenseTSDF(is_global_map=True, map_scale=[6.4, 6.4], voxel_scale=0.05, num_voxel_per_blk_axis=16,
+                                 max_ray_length=3.0, max_disp_particles=4096, max_submap_num=4)
+    m.set_dep_camera_intrinsic(K)
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    n = 48
+    Rs, Ts = syn.stream_poses(n, start=3, period=400, radius=0.08)
+    e = np.array([])
+    for q in range(n):
+        m.recast_depth_to_map(Rs[q], Ts[q], d, e)
+    keys = sorted(k for k, v in m.TSDF_observed.d.items() if v > 0)
+    g = {"K": np.array(K), "depth": d, "Rs": Rs, "Ts": Ts,
+         "idx": np.array([k[1:] for k in keys], np.int16), "T": np.array([m.TSDF.d[k] for k in keys], np.float32),
+         "W": np.array([m.W_TSDF.d[k] for k in keys], np.float32)}
+    print(len(keys), "voxels,", int((g["W"] >= 999.5).sum()), "at Wmax")
+    out = os.path.join(ROOT, "tests", "golden", "ref_exec_sat.npz")
+    np.savez_compressed(out, **g)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else ""
-    {"topo": topo, "f32": f32_state}.get(mode, main)()
+    {"topo": topo, "f32": f32_state, "sat": saturation}.get(mode, main)()

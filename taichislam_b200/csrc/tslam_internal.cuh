@@ -32,6 +32,7 @@
 #define TS_ERR_POOL_FULL 1
 #define TS_ERR_TABLE_FULL 2
 #define TS_ERR_RAYLIST_FULL 4
+#define TS_ERR_BUCKET_RANGE 8   // a point further than 4095 voxels from the sensor origin: beyond the bucket index's key range
 #define TS_PROF_RING 512
 #define TS_PROF_EV 8   // events per profiled integrate launch
 
@@ -287,8 +288,7 @@ struct TsMarchCtl {  // device-side control block of one launch (zeroed by k_mar
   int scale_k;       // shared-memory sums are kept in units of 2^-scale_k (k_seg_scan: largest k with max * 2^k < 2^30)
   int ticket;
   unsigned int tmp_cursor;  // next free entry of the segment-list pool
-  int ray_done;      // rays of the list that already have their record (ray set-up runs once per frame group)
-  int setup_ticket;
+  int pad0, pad1;
   int pad[3];
 };
 struct TsMarchWs {
@@ -322,7 +322,11 @@ struct tslam_tsdf {
   TsIntrin in;
   size_t table_cap;
   // integrate workspace
-  TsBucket* buckets;   // [TSLAM_MAX_BATCH * bucket_cap]
+  // per-frame bucket grid, split in two: a small open-addressing INDEX (8 B per entry: record slot + 39-bit key) that
+  // the bucket kernel probes, and the 64-byte RECORDS with the exact sums (every warp of the bucket kernel owns 32 of them), filled in the order the buckets
+  // are opened - so the ray set-up reads and zeroes them in short runs instead of 64 random bytes per ray
+  TsBucket* buckets;   // records [TSLAM_MAX_BATCH * bucket_cap]; frame f owns [f * bucket_cap, (f + 1) * bucket_cap)
+  unsigned long long* bidx;  // index [TSLAM_MAX_BATCH * bucket_cap]
   uint32_t bucket_cap; // power of two
   uint32_t* ray_list;  // [TSLAM_MAX_BATCH * max_rays_per_frame]
   uint32_t ray_list_cap;
@@ -364,7 +368,6 @@ struct tslam_tsdf {
   TsMarchWs mw;        // block-binned ray march workspace (tslam_march.cu)
   int march_mode;      // 0 = legacy k_raymarch, 1 = block-binned (default for untextured maps), env TSLAM_MARCH
   int march_verify;    // TSLAM_MARCH_VERIFY=1: every fast-path index is re-computed exactly, mismatches counted
-  int frame_group;     // frames per bucket / ray-set-up round of an integrate launch (TSLAM_FRAME_GROUP, default 8)
   bool clamp_on_commit;
   // frame queue of the per-frame API (tslam_tsdf_queue_depth): double-buffered device staging fed by a copy stream
   int q_n, q_buf, q_h, q_w;
@@ -456,5 +459,5 @@ int ts_check_deferred_async(tslam_tsdf* m, cudaStream_t st);  // same, after the
 // tslam_march.cu: block-binned ray march of the rays listed in m->ray_list (replaces k_raymarch<false>)
 int ts_march_alloc(tslam_tsdf* m);
 void ts_march_free(tslam_tsdf* m);
-int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, int g0);  // rays listed since the last call
+int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift);  // rays listed since the last call
 int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEvent_t* sub_ev);

@@ -52,19 +52,20 @@
 // K2a: ray set-up (process_new_pcl :240-251): one thread per bucket -> one 32-byte ray record
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* buckets,
-                                                    uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
-                                                    const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr, uint32_t g0) {
+                                                    unsigned long long* bidx, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
+                                                    const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr) {
   const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
-  const uint32_t r0 = (uint32_t)w.ctl->ray_done;  // rays of earlier frame groups of this launch
   const float vs = in.vs;
   unsigned int my_rays = 0, my_fmax = 0;
-  for (uint32_t r = r0 + blockIdx.x * 256 + threadIdx.x; r < n_rays; r += gridDim.x * 256) {
+  for (uint32_t r = blockIdx.x * 256 + threadIdx.x; r < n_rays; r += gridDim.x * 256) {
     const uint32_t id = ray_list[r];
-    const uint32_t f = g0 + (id >> bucket_shift);
+    const uint32_t f = id >> bucket_shift;
     TsBucket* bk = &buckets[id];
     const int cnt = bk->cnt;
     const long long sx = bk->sx, sy = bk->sy, sz = bk->sz, sd = bk->sd;
-    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
+    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its index entry back zeroed
+    const unsigned long long ie = bk->key;
+    if (ie) bidx[ie - 1ull] = 0ull;
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     uint4* q = reinterpret_cast<uint4*>(bk);
     q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
@@ -127,11 +128,6 @@ __global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBat
   if (threadIdx.x == 0) {
     if (s_rays) atomicAdd(&ctr->n_rays, (unsigned long long)s_rays);
     if (s_fmax) atomicMax(&w.ctl->fmax_bits, s_fmax);
-    __threadfence();
-    if (atomicAdd(&w.ctl->setup_ticket, 1) == (int)gridDim.x - 1) {  // last CTA: this group's rays are done
-      w.ctl->setup_ticket = 0;
-      w.ctl->ray_done = (int)n_rays;
-    }
   }
 }
 
@@ -756,11 +752,10 @@ void ts_march_free(tslam_tsdf* m) {
   cudaFree(w.cta_chunk);
 }
 
-// ray set-up of the rays listed since the last call (one frame group; g0 = its first frame)
-int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, int g0) {
+// ray set-up of the listed rays
+int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift) {
   if (!m->mw.rays) { int rca = ts_march_alloc(m); if (rca) return rca; }
-  k_ray_setup<<<m->sm_count * 16, 256, 0, st>>>(batch, m->in, m->g, m->buckets, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters,
-                                                (uint32_t)g0);
+  k_ray_setup<<<m->sm_count * 16, 256, 0, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }

@@ -39,28 +39,42 @@ extern "C" int tslam_device_count(void) {
   return n;
 }
 
+// bucket index entry: [record slot + 1 : 25][bx + 4096 : 13][by + 4096 : 13][bz + 4096 : 13]; 0 = empty
+#define BK_OFF 4096
+#define BK_KEY_BITS 39
+#define BK_KEY_MASK ((1ull << BK_KEY_BITS) - 1ull)
+#define BK_MAX_SLOTS ((1u << 25) - 2u)
 __device__ __forceinline__ unsigned long long bucket_key(int bx, int by, int bz) {
-  return ((((unsigned long long)(bx + (1 << 20)) << 42) | ((unsigned long long)(by + (1 << 20)) << 21) |
-           (unsigned long long)(bz + (1 << 20))) + 1ull);
+  return ((unsigned long long)(bx + BK_OFF) << 26) | ((unsigned long long)(by + BK_OFF) << 13) | (unsigned long long)(bz + BK_OFF);
 }
 
-// accumulate one unprojected point per lane into the frame's bucket table.
+// accumulate one unprojected point per lane into the frame's bucket grid.
 // process_point (dense_tsdf.py:227-234) with exact fixed-point sums.  Lanes of a warp that fall into
 // the same bucket (neighbouring pixels usually do) are merged first (match.any + redux): one probe and
-// one set of reductions per distinct bucket per warp instead of per pixel.  Must be called by all 32
-// lanes; `valid` masks lanes without a point.  Returns the table slot when this lane OPENED a bucket
-// (the bucket becomes one ray; the caller appends it to the ray list), else -1.
-__device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint32_t cap_mask, float px, float py, float pz, float dep,
+// one set of reductions per distinct bucket per warp instead of per pixel.  The index maps the bucket's
+// voxel to a RECORD slot.  Slots need no allocator: every warp owns the 32 records [slot_base, slot_base + 32)
+// (it holds at most 32 distinct buckets), a probing lane brings the slot of its rank along and publishes it
+// with the key in ONE 64-bit CAS, so nobody ever waits for a slot; the slot of a lane that finds its bucket
+// already open stays unused (zero record).
+// Must be called by all 32 lanes; `valid` masks lanes without a point.  Returns the record slot when this
+// lane OPENED a bucket (the bucket becomes one ray; the caller appends it to the ray list), else -1.
+__device__ __forceinline__ int bucket_accumulate(bool valid, unsigned long long* idx, uint32_t cap_mask, uint32_t idx_base, TsBucket* recs,
+                                                 uint32_t rec_cap, uint32_t slot_base, float px, float py, float pz, float dep,
                                                  float vs, bool agg_ok, int* err, bool tex = false, int cr = 0, int cg = 0, int cb = 0) {
-  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return -1;
   const int bx = iroundf(px / vs), by = iroundf(py / vs), bz = iroundf(pz / vs);  // xyz_to_ijk mapping_common.py:240-243
+  if (valid && ((unsigned)(bx + (BK_OFF - 1)) > 2u * (BK_OFF - 1) || (unsigned)(by + (BK_OFF - 1)) > 2u * (BK_OFF - 1) ||
+                (unsigned)(bz + (BK_OFF - 1)) > 2u * (BK_OFF - 1))) {
+    atomicOr(err, TS_ERR_BUCKET_RANGE);
+    valid = false;
+  }
   const unsigned long long key = bucket_key(bx, by, bz);
   long long qx = __float2ll_rn(px * FIXQ), qy = __float2ll_rn(py * FIXQ), qz = __float2ll_rn(pz * FIXQ), qd = __float2ll_rn(dep * FIXQ);
   int cnt = 1;
-  if (agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
+  bool act = valid;  // this lane probes and adds
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  if (valid && agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
     const unsigned grp = __match_any_sync(vmask, key);
-    const bool leader = (threadIdx.x & 31) == (__ffs(grp) - 1);
+    act = (threadIdx.x & 31) == (__ffs(grp) - 1);
     cnt = __popc(grp);
     if (cnt > 1) {
       qx = (long long)__reduce_add_sync(grp, (int)qx);
@@ -73,27 +87,30 @@ __device__ __forceinline__ int bucket_accumulate(bool valid, TsBucket* tab, uint
         cb = __reduce_add_sync(grp, cb);
       }
     }
-    if (!leader) return -1;
   }
   uint32_t h = ts_hash(key) & cap_mask;
-  TsBucket* b = nullptr;
-  int fresh = -1;
+  const unsigned amask = __ballot_sync(0xffffffffu, act);
+  if (!act) return -1;
+  const uint32_t my_slot = slot_base + (uint32_t)__popc(amask & ((1u << (threadIdx.x & 31)) - 1u));
+  if (my_slot >= rec_cap) { atomicOr(err, TS_ERR_RAYLIST_FULL); return -1; }
+  unsigned long long cur = ts_ld_volatile(&idx[h]);
+  int slot = -1, fresh = -1;
   for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
-    TsBucket* c = &tab[h];
-    unsigned long long cur = ts_ld_volatile(&c->key);
     if (cur == 0ull) {
-      const unsigned long long prev = atomicCAS(&c->key, 0ull, key);
+      const unsigned long long prev = atomicCAS(&idx[h], 0ull, ((unsigned long long)(my_slot + 1) << BK_KEY_BITS) | key);
       if (prev == 0ull) {  // this point opened the bucket: it becomes one ray
-        fresh = (int)h;
-        b = c;
+        slot = fresh = (int)my_slot;
+        recs[slot].key = (unsigned long long)(idx_base + h) + 1ull;  // where the consumer clears the index
         break;
       }
       cur = prev;
     }
-    if (cur == key) { b = c; break; }
+    if ((cur & BK_KEY_MASK) == key) { slot = (int)(cur >> BK_KEY_BITS) - 1; break; }
     h = (h + 1) & cap_mask;
+    cur = ts_ld_volatile(&idx[h]);
   }
-  if (!b) { atomicOr(err, TS_ERR_TABLE_FULL); return -1; }
+  if (slot < 0) { atomicOr(err, TS_ERR_TABLE_FULL); return -1; }
+  TsBucket* b = &recs[slot];
   red_add_u32((unsigned int*)&b->cnt, (unsigned int)cnt);
   red_add_u64((unsigned long long*)&b->sx, (unsigned long long)qx);
   red_add_u64((unsigned long long*)&b->sy, (unsigned long long)qy);
@@ -139,11 +156,11 @@ __device__ __forceinline__ void append_rays_cta(int fresh_slot, uint32_t tab_bas
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict__ depth, int frame_stride, int row_mul, int w, int hh, int ww,
                                                        const __grid_constant__ TsBatch batch, TsIntrin in, int agg_ok,
-                                                       TsBucket* buckets, uint32_t bucket_cap, uint32_t* ray_list,
-                                                       int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err,
-                                                       const uint8_t* __restrict__ tex, int th, int tw, int g0) {
-  const int tz = blockIdx.z;    // bucket table of this frame
-  const int f = g0 + tz;        // frame of the batch (g0 > 0: frame groups sharing the first tables, see ts_integrate_depth_impl)
+                                                       TsBucket* buckets, unsigned long long* bidx, uint32_t bucket_cap,
+                                                       uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr, int* err,
+                                                       const uint8_t* __restrict__ tex, int th, int tw) {
+  const int tz = blockIdx.z;    // frame of the batch = its bucket grid
+  const int f = tz;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ii = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
   const int jj = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
@@ -174,16 +191,16 @@ __global__ void __launch_bounds__(256) k_bucket_depth(const uint16_t* __restrict
     }
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets + (size_t)tz * bucket_cap, bucket_cap - 1, px, py, pz, dep, in.vs, agg_ok != 0, err,
-                                      tex != nullptr, cr, cg, cb);
+  const int fresh = bucket_accumulate(valid, bidx + (size_t)tz * bucket_cap, bucket_cap - 1, (uint32_t)tz * bucket_cap, buckets + (size_t)tz * bucket_cap,
+                                      bucket_cap, ((blockIdx.y * gridDim.x + blockIdx.x) * 8u + (uint32_t)wid) * 32u, px, py, pz, dep, in.vs, agg_ok != 0, err, tex != nullptr, cr, cg, cb);
   append_rays_cta(fresh, (uint32_t)tz * bucket_cap, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(&ctr->n_px, (unsigned long long)(hh * ww));
 }
 
 // K1b: point cloud -> buckets.  recast_pcl_to_map_kernel (dense_tsdf.py:167-185).
 __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__ xyz, int n, const __grid_constant__ TsBatch batch,
-                                                        TsIntrin in, int agg_ok, TsBucket* buckets, uint32_t bucket_cap,
-                                                        uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
+                                                        TsIntrin in, int agg_ok, TsBucket* buckets, unsigned long long* bidx,
+                                                        uint32_t bucket_cap, uint32_t rec_cap, uint32_t* ray_list, int* n_rays, uint32_t ray_cap, TsCounters* ctr,
                                                         int* err, const uint8_t* __restrict__ rgb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int cr = 0, cg = 0, cb = 0;
@@ -200,7 +217,8 @@ __global__ void __launch_bounds__(256) k_bucket_points(const float* __restrict__
     if (rgb) { cr = rgb[3 * (size_t)t]; cg = rgb[3 * (size_t)t + 1]; cb = rgb[3 * (size_t)t + 2]; }  // :179-182
   }
   const unsigned nv = __popc(__ballot_sync(0xffffffffu, valid));
-  const int fresh = bucket_accumulate(valid, buckets, bucket_cap - 1, px, py, pz, len, in.vs, agg_ok != 0, err, rgb != nullptr, cr, cg, cb);  // :183/:185
+  const int fresh = bucket_accumulate(valid, bidx, bucket_cap - 1, 0u, buckets, rec_cap, (uint32_t)(t & ~31), px, py, pz, len, in.vs, agg_ok != 0, err,
+                                      rgb != nullptr, cr, cg, cb);  // :183/:185
   append_rays_cta(fresh, 0u, nv, ray_list, n_rays, ray_cap, ctr, err);
   if (t == 0) atomicAdd(&ctr->n_px, (unsigned long long)n);
 }
@@ -239,8 +257,9 @@ __device__ __forceinline__ void win_add(unsigned int* lo, int* hi, int x) {
 
 template <bool TEX>
 __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
-                                                              TsBucket* buckets, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
-                                                              const int* __restrict__ n_rays_p, uint32_t ray_cap, TsCounters* ctr) {
+                                                              TsBucket* buckets, unsigned long long* bidx, uint32_t bucket_shift,
+                                                              const uint32_t* __restrict__ ray_list, const int* __restrict__ n_rays_p, uint32_t ray_cap,
+                                                              TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned int win[];  // [4][4096]: A.lo, A.hi, B.lo, B.hi
   unsigned int* const w_alo = win;
   int* const w_ahi = (int*)(win + RM_WIN3);
@@ -285,7 +304,9 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_raymarch(const __grid_constan
       cnt = bk->cnt;
       sx = bk->sx; sy = bk->sy; sz = bk->sz; sd = bk->sd;
       if (TEX) { ccr = bk->cr; ccg = bk->cg; ccb = bk->cb; }
-      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the slot back zeroed
+      // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its index entry back zeroed
+      const unsigned long long ie = bk->key;
+      if (ie) bidx[ie - 1ull] = 0ull;
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       uint4* q = reinterpret_cast<uint4*>(bk);
       q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
@@ -747,12 +768,14 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
   m->bucket_cap = (uint32_t)next_pow2(sampled + sampled / 2);
   if (const char* bc = getenv("TSLAM_BUCKET_CAP")) { if (atoi(bc) >= 1024) m->bucket_cap = (uint32_t)next_pow2((size_t)atoi(bc)); }  // experiment
   // the point-cloud path treats the TSLAM_MAX_BATCH per-frame tables as ONE table
-  if ((size_t)m->cfg.max_points * 3 / 2 > (size_t)TSLAM_MAX_BATCH * m->bucket_cap) {
+  if ((size_t)m->cfg.max_points * 3 / 2 > (size_t)TSLAM_MAX_BATCH * m->bucket_cap || (size_t)m->cfg.max_points > BK_MAX_SLOTS || m->bucket_cap > BK_MAX_SLOTS) {
     ts_set_error("max_points=%d too large for the bucket workspace", m->cfg.max_points);
     return TSLAM_E_INVALID;
   }
   TS_CUDA(cudaMalloc(&m->buckets, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
   TS_CUDA(cudaMemset(m->buckets, 0, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * sizeof(TsBucket)));
+  TS_CUDA(cudaMalloc(&m->bidx, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * 8));
+  TS_CUDA(cudaMemset(m->bidx, 0, (size_t)TSLAM_MAX_BATCH * m->bucket_cap * 8));
   m->ray_list_cap = (uint32_t)((size_t)TSLAM_MAX_BATCH * sampled);
   if (m->ray_list_cap < (uint32_t)m->cfg.max_points) m->ray_list_cap = (uint32_t)m->cfg.max_points;
   TS_CUDA(cudaMalloc(&m->ray_list, (size_t)m->ray_list_cap * 4));
@@ -813,8 +836,6 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     const char* mm = getenv("TSLAM_MARCH");
     m->march_mode = (m->cfg.texture_enabled || (mm && mm[0] == 'l') || m->cfg.max_ray_length / m->cfg.voxel_scale > 60000.0) ? 0 : 1;
     m->march_verify = getenv("TSLAM_MARCH_VERIFY") != nullptr;
-    m->frame_group = TSLAM_MAX_BATCH;  // one round per launch (rounds of 4/8/16 frames were measured: no gain, see profiles/r02_march.md)
-    if (const char* fg = getenv("TSLAM_FRAME_GROUP")) { const int v = atoi(fg); if (v >= 1 && v <= TSLAM_MAX_BATCH) m->frame_group = v; }
     // (the march workspace - ~2 GB for 640x480 frames - is allocated by the first integrate launch: global maps that are
     // only ever fused into never pay for it)
   }
@@ -840,7 +861,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   if (m->tex_stage) cudaFree(m->tex_stage);
   if (m->rgb_stage) cudaFree(m->rgb_stage);
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.esdf_dirty); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
-  cudaFree(m->buckets); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
+  cudaFree(m->buckets); cudaFree(m->bidx); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
   if (m->mw.rays) ts_march_free(m);
@@ -938,6 +959,7 @@ int ts_check_deferred(tslam_tsdf* m) {
     int zero = 0;
     cudaMemcpy(m->g.err, &zero, 4, cudaMemcpyHostToDevice);
     if (err & TS_ERR_POOL_FULL) { ts_set_error("voxel-block pool exhausted (max_blocks=%d): samples were dropped", m->g.max_blocks); return TSLAM_E_POOL_FULL; }
+    if (err & TS_ERR_BUCKET_RANGE) { ts_set_error("a point lies more than 4095 voxels from the sensor origin (bucket key range): dropped"); return TSLAM_E_CAPACITY; }
     ts_set_error("device error flags 0x%x (hash table / ray list capacity)", err);
     return TSLAM_E_CAPACITY;
   }
@@ -1046,35 +1068,26 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
     const int agg_ok = m->cfg.max_ray_length < 30.0 ? 1 : 0;  // 32-lane int32 sums: |p| <= max_ray * sqrt(1 + tan^2) < 64 m even at 60 deg half-FOV
+    dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
+    if ((size_t)grid1.x * grid1.y * 256 > m->bucket_cap) {  // every 8x4-pixel warp tile owns 32 bucket records of its frame
+      ts_set_error("frame %dx%d (sampled %dx%d) has too many partial pixel tiles for max_image_pixels=%d", h, w, hh, ww, m->cfg.max_image_pixels);
+      return TSLAM_E_INVALID;
+    }
+    k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bidx,
+                                          m->bucket_cap, m->ray_list, m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw);
+    TS_LAUNCH_CHECK(m);
+    if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
     if (!m->g.cword && m->march_mode) {
-      // TSLAM_FRAME_GROUP < 64 runs bucket + ray set-up in rounds of that many frames sharing the first bucket tables
-      // (they then stay L2-resident between the kernel that fills them and the one that drains them).  Experiment
-      // knob: measured 4/8/16/64 frames per round -> 0.43/0.32/0.28/0.28 ms for the two kernels, so the default is one round.
-      const int G = m->frame_group;
-      for (int g0 = 0; g0 < nf; g0 += G) {
-        const int ng = nf - g0 < G ? nf - g0 : G;
-        dim3 grid1((ww + 31) / 32, (hh + 7) / 8, ng);
-        k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap,
-                                              m->ray_list, m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw, g0);
-        TS_LAUNCH_CHECK(m);
-        if (pe && g0 + ng >= nf) TS_CUDA(cudaEventRecord(pe[1], st));  // (one round: pe[1]..pe[4] is the ray set-up)
-        int rcs = ts_march_setup(m, st, batch, bshift, g0);
-        if (rcs) return rcs;
-      }
+      int rcs = ts_march_setup(m, st, batch, bshift);
+      if (rcs) return rcs;
       int rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
       if (rcm) return rcm;
+    } else if (m->g.cword) {
+      k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,
+                                                                     m->ray_list_cap, m->counters);
     } else {
-      dim3 grid1((ww + 31) / 32, (hh + 7) / 8, nf);
-      k_bucket_depth<<<grid1, 256, 0, st>>>(src, rows_stored * w, rows_compacted ? 1 : step, w, hh, ww, batch, m->in, agg_ok, m->buckets, m->bucket_cap, m->ray_list,
-                                            m->n_rays, m->ray_list_cap, m->counters, m->g.err, tsrc, th, tw, 0);
-      TS_LAUNCH_CHECK(m);
-      if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
-      if (m->g.cword)
-        k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                       m->ray_list_cap, m->counters);
-      else
-        k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
-                                                                                       m->ray_list_cap, m->counters);
+      k_raymarch<false><<<(m->sm_count - m->rm_reserve) * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,
+                                                                                     m->ray_list_cap, m->counters);
     }
     TS_LAUNCH_CHECK(m);
     if (pe) TS_CUDA(cudaEventRecord(pe[2], st));
@@ -1121,23 +1134,24 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
   }
   const uint32_t bshift = 31;  // every ray belongs to batch.f[0]
   const uint32_t cap_total = (uint32_t)TSLAM_MAX_BATCH * m->bucket_cap;  // power of two
+  const uint32_t rec_cap = cap_total < BK_MAX_SLOTS ? cap_total : BK_MAX_SLOTS;
   cudaEvent_t* pe = m->profiling ? m->ev + TS_PROF_EV * (m->prof_launches % TS_PROF_RING) : nullptr;
     if (pe) TS_CUDA(cudaEventRecord(pe[0], st));
   const int agg_ok = m->cfg.max_ray_length < 30.0 ? 1 : 0;  // 32-lane int32 sums: |p| <= max_ray * sqrt(1 + tan^2) < 64 m even at 60 deg half-FOV
-  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, cap_total, m->ray_list, m->n_rays,
+  k_bucket_points<<<(n + 255) / 256, 256, 0, st>>>(src, n, batch, m->in, agg_ok, m->buckets, m->bidx, cap_total, rec_cap, m->ray_list, m->n_rays,
                                                     m->ray_list_cap, m->counters, m->g.err, csrc);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[1], st));
   if (m->g.cword)
-    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+    k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,
                                                                    m->ray_list_cap, m->counters);
   else if (m->march_mode) {
-    int rcm = ts_march_setup(m, st, batch, bshift, 0);
+    int rcm = ts_march_setup(m, st, batch, bshift);
     if (rcm) return rcm;
     rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
     if (rcm) return rcm;
   } else
-    k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, bshift, m->ray_list, m->n_rays,
+    k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,
                                                                     m->ray_list_cap, m->counters);
   TS_LAUNCH_CHECK(m);
   if (pe) TS_CUDA(cudaEventRecord(pe[2], st));

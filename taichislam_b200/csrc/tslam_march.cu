@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(1024) k_seg_scan(TsMarchWs w, TsCounters* ctr)
 // K2e: placement.  Same grid as k_seg_walk: CTA i moves the segments of its list into the blocks' runs:
 // seg_off[block] + seg_rel[block, class] + cursor (warp-aggregated global atomic on seg_count, zero on entry).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(MS_THREADS) k_seg_place(TsMarchWs w) {
+#define PL_THREADS 1024  // the kernel waits on one returning atomic per (warp, key): more warps per list hide it
+__global__ void __launch_bounds__(PL_THREADS) k_seg_place(TsMarchWs w) {
   __shared__ uint32_t s_chunk[WK_MAXCH];
   const uint32_t cta = blockIdx.x;
   const int total = w.cta_n[cta];
@@ -392,10 +393,10 @@ __global__ void __launch_bounds__(MS_THREADS) k_seg_place(TsMarchWs w) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t* cch = w.cta_chunk + (size_t)cta * WK_MAXCH;
   const int nch = (total + WK_CHUNK - 1) / WK_CHUNK;
-  for (int k = threadIdx.x; k < nch; k += MS_THREADS) s_chunk[k] = cch[k];
+  for (int k = threadIdx.x; k < nch; k += PL_THREADS) s_chunk[k] = cch[k];
   __syncthreads();
   const bool overflow = w.ctl->overflow != 0;  // work list did not fit: every segment goes to the generic path
-  for (int p0 = (threadIdx.x & ~31); p0 < total; p0 += MS_THREADS) {
+  for (int p0 = (threadIdx.x & ~31); p0 < total; p0 += PL_THREADS) {
     const int p = p0 + (int)lane;
     const bool have = p < total;
     TsSeg sg = TsSeg{0u, 0u};
@@ -470,7 +471,7 @@ __device__ __forceinline__ double mb_sum(unsigned int lo, int hi) {
   return (double)((long long)hi * 65536ll + (long long)(unsigned int)(lo - ((unsigned int)hi << 16)));
 }
 
-template <bool VERIFY, int MB_THREADS, int MB_MINB, bool RET>
+template <bool VERIFY, int MB_THREADS, int MB_MINB>
 __global__ void __launch_bounds__(MB_THREADS, MB_MINB) k_march_blocks(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsMarchWs w,
                                                                  TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned int mb_smem[];
@@ -537,67 +538,86 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) k_march_blocks(const __gr
       const float L0 = __fmaf_rn(-jf, vs, a.w);
       const float wf = b.w * fix;  // w in fixed-point units (exact: power of two)
       const int wq = __float2int_rn(wf);
-      const bool tiny = wq < MB_MIN_WQ;  // weight far below the launch's largest: f32 reductions keep its relative precision
+      const int wqh = wq >> 16;
+      // weight far below the launch's largest (f32 reductions keep its relative precision), blocks cut by the volume
+      // boundary, VERIFY: every sample of the segment takes the exact path below
+      const bool all_slow = wq < MB_MIN_WQ || partial || VERIFY;
       const float cntf = (float)cnt;
-      float kf = 0.0f;
-      if (cnt > 1) kf = (float)((int)(lane * 7u) % cnt);  // staggered start
-      auto sample = [&](const bool pred, auto PARTIAL) __attribute__((always_inline)) {
-        const float gx = __fmaf_rn(ux, kf, x0), gy = __fmaf_rn(uy, kf, y0), gz = __fmaf_rn(uz, kf, z0);
-        // round to nearest + distance of the fraction from .5 (magic-number rounding: |g| < 2^22)
-        const float tx = gx + 12582912.0f, ty = gy + 12582912.0f, tz = gz + 12582912.0f;
-        int lx = __float_as_int(tx) - 0x4B400000, ly = __float_as_int(ty) - 0x4B400000, lz = __float_as_int(tz) - 0x4B400000;
-        const float rx = gx - (tx - 12582912.0f), ry = gy - (ty - 12582912.0f), rz = gz - (tz - 12582912.0f);
-        const bool near = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) > eps_hi;
-        bool ok = pred;
-        const bool slow = pred && (near || (((unsigned)(lx | ly | lz)) > 15u) || tiny || VERIFY);
-        const float ds = __fmaf_rn(-kf, vs, L0);  // L - j*vs
-        const float avq = wf * ds;                 // w * ds (:264) in fixed-point units
-        if (__any_sync(FULL, slow)) {
-          if (slow) {  // exact index (:253-254); a sample that really lies in another block goes through the global path
-            int xi, yi, zi;
-            exact_index(ux, uy, uz, batch.f[frame].T, j0 + (int)kf, vs, rvs, xi, yi, zi);
-            const int ex = xi - ox, ey = yi - oy, ez = zi - oz;
-            if (VERIFY && !near && (ex != lx || ey != ly || ez != lz)) my_bad++;
-            if (near) my_slow++;
-            lx = ex; ly = ey; lz = ez;
-            if (tiny || ((unsigned)(lx | ly | lz)) > 15u) {
-              ok = false;
-              my_fb++;
-              global_sample(g, sm, xi, yi, zi, (float)((double)avq * unfix), (float)((double)wf * unfix), my_upd, my_oob);
-            }
-          }
-        }
-        if (decltype(PARTIAL)::value && ok) {
-          const int xi = lx + ox, yi = ly + oy, zi = lz + oz;
-          if (!((unsigned)(xi + g.hN) < (unsigned)g.N && (unsigned)(yi + g.hN) < (unsigned)g.N && (unsigned)(zi + g.hNz) < (unsigned)g.Nz)) {
-            ok = false;
-            my_oob++;
-          }
-        }
-        if (ok) {
-          const int e = lx * MB_SX + ly * MB_SY + lz;
-          const int xq = __float2int_rn(avq);
-          if (RET) {  // lo/hi with carry: two returning atomics + a rare third
-            const unsigned int oa = atomicAdd(&a_lo[e], (unsigned int)xq);
-            const int ca = (xq >> 31) + ((oa + (unsigned int)xq) < oa ? 1 : 0);
-            if (ca) atomicAdd(&a_hi[e], ca);
-            const unsigned int ob = atomicAdd(&b_lo[e], (unsigned int)wq);
-            if ((ob + (unsigned int)wq) < ob) atomicAdd(&b_hi[e], 1);
-          } else {
+      int k0 = 0;
+      if (cnt > 1) k0 = (int)(lane * 7u) % cnt;  // staggered start
+      float kf = (float)k0;
+      my_upd += (unsigned)cnt;
+      // ---- fast loop: branch-free.  Iteration i of a lane handles step (k0 + i) mod cnt of its segment.  A sample
+      // whose rounding is not certain (|fraction - .5| < near_eps) or whose voxel is not in this block only sets bit i
+      // of slow_mask; those are redone exactly after the loop.
+      unsigned slow_mask = 0u;
+      if (all_slow) slow_mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+      else {
+        for (int i = 0; i < maxc; ++i) {
+          const float gx = __fmaf_rn(ux, kf, x0), gy = __fmaf_rn(uy, kf, y0), gz = __fmaf_rn(uz, kf, z0);
+          // round to nearest + distance of the fraction from .5 (magic-number rounding: |g| < 2^22): the low mantissa
+          // bits of t hold the block-local voxel coordinate
+          const float tx = gx + 12582912.0f, ty = gy + 12582912.0f, tz = gz + 12582912.0f;
+          const float rx = gx - (tx - 12582912.0f), ry = gy - (ty - 12582912.0f), rz = gz - (tz - 12582912.0f);
+          const unsigned qx = __float_as_uint(tx), qy = __float_as_uint(ty), qz = __float_as_uint(tz);
+          const bool inb = ((qx | qy | qz) - 0x4B400000u) <= 15u;  // all three coordinates in [0, 16)
+          const bool sure = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) <= eps_hi;
+          const bool pred = i < cnt;
+          const float avq = __fmaf_rn(-kf, vs, L0) * wf;  // w * ds, ds = L - j*vs (:258-264), in fixed-point units
+          if (pred && inb && sure) {
+            const unsigned e = qx * (unsigned)MB_SX + qy * (unsigned)MB_SY + qz - 0x4B400000u * (unsigned)(MB_SX + MB_SY + 1);
+            const int xq = __float2int_rn(avq);
             atomicAdd(&a_lo[e], (unsigned int)xq);
             atomicAdd(&a_hi[e], xq >> 16);
             atomicAdd(&b_lo[e], (unsigned int)wq);
-            atomicAdd(&b_hi[e], wq >> 16);
+            atomicAdd(&b_hi[e], wqh);
+          } else if (pred) {
+            slow_mask |= 1u << i;
           }
-          my_upd++;
+          kf += 1.0f;
+          if (kf >= cntf) kf = 0.0f;
         }
-        kf += 1.0f;
-        if (kf >= cntf) kf = 0.0f;
-      };
-      if (partial) {
-        for (int i = 0; i < maxc; ++i) sample(i < cnt, std::true_type{});
-      } else {
-        for (int i = 0; i < maxc; ++i) sample(i < cnt, std::false_type{});
+      }
+      // ---- exact path (:253-254) for the flagged samples; a sample that really lies in another block, is out of
+      // bounds or carries a tiny weight goes through the global path
+      if (__any_sync(FULL, slow_mask != 0u)) {
+        const bool tiny = wq < MB_MIN_WQ;
+        while (slow_mask) {
+          const int i = __ffs(slow_mask) - 1;
+          slow_mask &= slow_mask - 1u;
+          int k = k0 + i;
+          if (k >= cnt) k -= cnt;
+          const float kk = (float)k;
+          const float avq = __fmaf_rn(-kk, vs, L0) * wf;
+          int xi, yi, zi;
+          exact_index(ux, uy, uz, batch.f[frame].T, j0 + k, vs, rvs, xi, yi, zi);
+          const int lx = xi - ox, ly = yi - oy, lz = zi - oz;
+          if (VERIFY || !all_slow) {
+            const float gx = __fmaf_rn(ux, kk, x0), gy = __fmaf_rn(uy, kk, y0), gz = __fmaf_rn(uz, kk, z0);
+            const float tx = gx + 12582912.0f, ty = gy + 12582912.0f, tz = gz + 12582912.0f;
+            const float rx = gx - (tx - 12582912.0f), ry = gy - (ty - 12582912.0f), rz = gz - (tz - 12582912.0f);
+            const bool near = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) > eps_hi;
+            if (near) my_slow++;
+            if (VERIFY && !near && (lx != __float_as_int(tx) - 0x4B400000 || ly != __float_as_int(ty) - 0x4B400000 || lz != __float_as_int(tz) - 0x4B400000)) my_bad++;
+          }
+          bool local = !tiny && ((unsigned)(lx | ly | lz)) <= 15u;
+          if (!local) my_fb++;
+          if (local && partial &&
+              !((unsigned)(xi + g.hN) < (unsigned)g.N && (unsigned)(yi + g.hN) < (unsigned)g.N && (unsigned)(zi + g.hNz) < (unsigned)g.Nz)) {
+            local = false;  // global_sample counts it as out of bounds
+          }
+          if (local) {
+            const int e = lx * MB_SX + ly * MB_SY + lz;
+            const int xq = __float2int_rn(avq);
+            atomicAdd(&a_lo[e], (unsigned int)xq);
+            atomicAdd(&a_hi[e], xq >> 16);
+            atomicAdd(&b_lo[e], (unsigned int)wq);
+            atomicAdd(&b_hi[e], wqh);
+          } else {
+            my_upd--;
+            global_sample(g, sm, xi, yi, zi, (float)((double)avq * unfix), (float)((double)wf * unfix), my_upd, my_oob);
+          }
+        }
       }
     }
     __syncthreads();
@@ -611,8 +631,7 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) k_march_blocks(const __gr
       const unsigned int alo = a_lo[e];
       const int ahi = a_hi[e];
       a_lo[e] = 0u; a_hi[e] = 0; b_lo[e] = 0u; b_hi[e] = 0;
-      if (RET) red_add_f32x2(&acc[v], (float)(((double)ahi * 4294967296.0 + (double)alo) * unfix), (float)(((double)bhi * 4294967296.0 + (double)blo) * unfix));
-      else red_add_f32x2(&acc[v], (float)(mb_sum(alo, ahi) * unfix), (float)(mb_sum(blo, bhi) * unfix));
+      red_add_f32x2(&acc[v], (float)(mb_sum(alo, ahi) * unfix), (float)(mb_sum(blo, bhi) * unfix));
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -739,9 +758,8 @@ int ts_march_alloc(tslam_tsdf* m) {
   const char* ee = getenv("TSLAM_NEAR_EPS");
   if (ee) eps = atof(ee);
   w.near_eps = (float)eps;
-  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false, 320, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
-  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false, 320, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
-  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<true, 320, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<false, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  TS_CUDA(cudaFuncSetAttribute(k_march_blocks<true, 320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
   return TSLAM_OK;
 }
 
@@ -772,14 +790,12 @@ int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEv
   k_seg_scan<<<1, 1024, 0, st>>>(m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[1], st));
-  k_seg_place<<<gx, MS_THREADS, 0, st>>>(m->mw);
+  k_seg_place<<<gx, PL_THREADS, 0, st>>>(m->mw);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[2], st));
-  static const bool vret = getenv("TSLAM_MB_RET") != nullptr;  // A/B: returning lo atomics + carry instead of 4 no-return atomics
   const int grid = (sms - m->rm_reserve) * 3;
-  if (m->march_verify) k_march_blocks<true, 320, 3, false><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
-  else if (vret) k_march_blocks<false, 320, 3, true><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
-  else k_march_blocks<false, 320, 3, false><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
+  if (m->march_verify) k_march_blocks<true, 320, 3><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
+  else k_march_blocks<false, 320, 3><<<grid, 320, MB_SMEM, st>>>(batch, m->in, m->g, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   k_march_generic<<<sms * 2, 256, 0, st>>>(batch, m->in, m->g, m->mw, m->counters);
   TS_LAUNCH_CHECK(m);

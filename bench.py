@@ -436,14 +436,22 @@ def main():
         host_t = torch.from_numpy(np.ascontiguousarray(make_inputs(BATCH, t_rank)[0]).view(np.int16))
 
         def run_e2e(mode, steps):
-            m = DenseTSDF(map_scale=MAP_SCALE, voxel_scale=0.05, num_voxel_per_blk_axis=16, is_global_map=True)
+            if mode == "dma_pageable":
+                os.environ["TSLAM_FRAME_COPY"] = "dma"  # read when the handle is created
+            try:
+                m = DenseTSDF(map_scale=MAP_SCALE, voxel_scale=0.05, num_voxel_per_blk_axis=16, is_global_map=True)
+            finally:
+                os.environ.pop("TSLAM_FRAME_COPY", None)
+            return run_e2e_on(m, mode, steps)
+
+        def run_e2e_on(m, mode, steps):
             m.set_dep_camera_intrinsic(syn.K_DEPTH)
             m.set_base_pose_submap(0, np.eye(3), np.zeros(3))  # pose-table rows start at zero (mapping_common.py:106-107)
             if mode == "borrow":
                 m.set_frame_borrowing(True)
             if mode == "commit1":
                 m.set_commit_granularity(1)
-            host = host_t.clone() if mode == "pageable" else host_t.pin_memory()
+            host = host_t.clone() if mode in ("pageable", "dma_pageable") else host_t.pin_memory()
             host_np = host.numpy().view(np.uint16)
             t = t_rank + 51200
             eRs, eTs = syn.stream_poses((args.warmup + steps) * STEP_FRAMES, start=t)
@@ -481,13 +489,17 @@ def main():
             vb, _ = run_e2e("borrow", es2)
             vp, _ = run_e2e("pageable", es2)
             vc, _ = run_e2e("commit1", es2)
+            vd, _ = run_e2e("dma_pageable", es2)
             e2e_modes = {"borrowed_pinned_frames": {"value": vb, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
                                                     "note": "opt-in set_frame_borrowing(True): no copy, the GPU reads the sampled rows from host "
                                                             "memory; frames must stay untouched until the next flush"},
                          "commit_every_frame": {"value": vc, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
                                                 "note": "set_commit_granularity(1): one launch sequence + commit per frame (Wmax clamp granule = frame)"},
-                         "pageable_frames": {"value": vp, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
-                                             "note": "what np.frombuffer(depth_msg.data) gives the ROS node (taichislam_node.py:381-382)"}}
+                         "pageable_frames": {"value": vp, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
+                                             "note": "what np.frombuffer(depth_msg.data) gives the ROS node (taichislam_node.py:381-382): the sampled "
+                                                     "rows are memcpy'd into the library's page-locked ring and fetched from there by the GPU"},
+                         "pageable_frames_through_cudaMemcpyAsync": {"value": vd, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
+                                                                     "note": "TSLAM_FRAME_COPY=dma: the runtime stages the whole pageable frame (A/B for the ring)"}}
         except Exception as ex:  # pragma: no cover
             e2e = e2e or {"value": None, "unit": UNIT, "error": repr(ex)}
             e2e_modes["error"] = repr(ex)

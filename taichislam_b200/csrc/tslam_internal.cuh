@@ -340,7 +340,14 @@ struct tslam_tsdf {
   // k_gather_rows in groups of TS_GATHER_GROUP frames (q_gathered = frames already handed to a gather launch)
   const uint16_t* q_hptr[TSLAM_MAX_BATCH];
   int q_gathered;
-  int zero_copy;  // 0 = off (TSLAM_ZERO_COPY=0)
+  int zero_copy;  // 1 = borrow page-locked frames (tslam_tsdf_set_frame_mode / TSLAM_ZERO_COPY=1); 0 = copy (default)
+  // pageable frames: the call copies the SAMPLED ROWS of the frame into this page-locked ring on the host (the caller
+  // may reuse its buffer at once) and the GPU fetches them from there like a borrowed frame
+  uint16_t* h_ring;       // [2][TSLAM_MAX_BATCH][ring_frame_cap] host, mapped
+  uint16_t* h_ring_dev;   // its device alias
+  size_t ring_frame_cap;  // elements per frame slot
+  int stage_mode;         // 1 = pageable frames through the ring (default), 0 = through cudaMemcpyAsync (TSLAM_FRAME_COPY=dma)
+  int q_sstride[TSLAM_MAX_BATCH];  // source row stride of the queued frame in 16-byte units
   int queue_launch[2];  // frames per queue launch, alternating (TSLAM_QUEUE_LAUNCH="a,b", default 32,32)
   int q_phase;          // which of the two thresholds the current launch uses (back to 0 at every flush)
   int trace;         // TSLAM_TRACE=1: print a per-launch timeline of the queue (debug)

@@ -384,10 +384,11 @@ __global__ void __launch_bounds__(1024) k_seg_scan(TsMarchWs w, TsCounters* ctr)
 // K2e: placement.  Same grid as k_seg_walk: CTA i moves the segments of its list into the blocks' runs:
 // seg_off[block] + seg_rel[block, class] + cursor (warp-aggregated global atomic on seg_count, zero on entry).
 // ---------------------------------------------------------------------------
+#define PL_SPLIT 2
 #define PL_THREADS 1024  // the kernel waits on one returning atomic per (warp, key): more warps per list hide it
 __global__ void __launch_bounds__(PL_THREADS) k_seg_place(TsMarchWs w) {
   __shared__ uint32_t s_chunk[WK_MAXCH];
-  const uint32_t cta = blockIdx.x;
+  const uint32_t cta = blockIdx.x / PL_SPLIT, part = blockIdx.x % PL_SPLIT;  // PL_SPLIT CTAs share one walk list
   const int total = w.cta_n[cta];
   if (total == 0) return;
   const uint32_t lane = threadIdx.x & 31u;
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_seg_place(TsMarchWs w) {
   for (int k = threadIdx.x; k < nch; k += PL_THREADS) s_chunk[k] = cch[k];
   __syncthreads();
   const bool overflow = w.ctl->overflow != 0;  // work list did not fit: every segment goes to the generic path
-  for (int p0 = (threadIdx.x & ~31); p0 < total; p0 += PL_THREADS) {
+  for (int p0 = (int)(part * PL_THREADS + (threadIdx.x & ~31)); p0 < total; p0 += PL_SPLIT * PL_THREADS) {
     const int p = p0 + (int)lane;
     const bool have = p < total;
     TsSeg sg = TsSeg{0u, 0u};
@@ -739,8 +740,8 @@ int ts_march_alloc(tslam_tsdf* m) {
   TS_CUDA(cudaMalloc(&w.items, (size_t)w.item_cap * sizeof(TsItem)));
   w.gen_cap = (uint32_t)(nr > (1u << 20) ? nr : (1u << 20));
   TS_CUDA(cudaMalloc(&w.gen, (size_t)w.gen_cap * sizeof(TsSeg)));
-  w.walk_x_max = m->sm_count * 3;
-  const size_t ncta = (size_t)w.walk_x_max + TSLAM_MAX_BATCH + 8;  // gx * nf <= 3 * SMs + nf
+  w.walk_x_max = m->sm_count * 3;  // one segment list per CTA (5 CTAs per SM measured slower: the per-(block, class) counters are the limit)
+  const size_t ncta = (size_t)w.walk_x_max + TSLAM_MAX_BATCH + 8;
   TS_CUDA(cudaMalloc(&w.cta_n, ncta * 4));
   TS_CUDA(cudaMemset(w.cta_n, 0, ncta * 4));
   TS_CUDA(cudaMalloc(&w.cta_chunk, ncta * WK_MAXCH * 4));
@@ -790,7 +791,7 @@ int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEv
   k_seg_scan<<<1, 1024, 0, st>>>(m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[1], st));
-  k_seg_place<<<gx, PL_THREADS, 0, st>>>(m->mw);
+  k_seg_place<<<gx * PL_SPLIT, PL_THREADS, 0, st>>>(m->mw);
   TS_LAUNCH_CHECK(m);
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[2], st));
   const int grid = (sms - m->rm_reserve) * 3;

@@ -791,6 +791,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     // host memory a few calls later - is opt-in: tslam_tsdf_set_frame_mode(m, 1) or TSLAM_ZERO_COPY=1.
     const char* zc = getenv("TSLAM_ZERO_COPY");
     m->zero_copy = (zc && zc[0] == '1') ? 1 : 0;
+    const char* fc = getenv("TSLAM_FRAME_COPY");  // "dma": pageable frames through cudaMemcpyAsync too (A/B against the ring)
+    m->stage_mode = (fc && strcmp(fc, "dma") == 0) ? 0 : 1;
     m->trace = getenv("TSLAM_TRACE") != nullptr;
     if (m->trace) {
       for (int i = 0; i < 2; i++)
@@ -863,6 +865,7 @@ extern "C" int tslam_tsdf_destroy(tslam_tsdf_t* m) {
   cudaFree(g.ghost); cudaFree(g.dirty_flag); cudaFree(g.esdf_dirty); cudaFree(g.dirty_list); cudaFree(m->scratch_i);
   cudaFree(m->buckets); cudaFree(m->bidx); cudaFree(m->ray_list); cudaFree(m->depth_stage); cudaFree(m->points_stage);
   cudaStreamDestroy(m->copy_stream);
+  if (m->h_ring) cudaFreeHost(m->h_ring);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_free[i]); }
   if (m->mw.rays) ts_march_free(m);
   cudaFree(m->counters); cudaFree(m->pose_R); cudaFree(m->pose_T); cudaFree(m->colormap);
@@ -1180,10 +1183,12 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
 struct TsGatherArgs {
   const uint4* src[TS_GATHER_GROUP];
   uint4* dst[TS_GATHER_GROUP];
+  int sstride[TS_GATHER_GROUP];  // source row stride (16-byte units): recast_step rows for a caller's frame, 1 row for the ring
 };
 __global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ TsGatherArgs ga, int hh, int row_u4, int row_stride_u4) {
   const uint4* __restrict__ src = ga.src[blockIdx.y];
   uint4* __restrict__ dst = ga.dst[blockIdx.y];
+  const int sstride = ga.sstride[blockIdx.y];
   const int total = hh * row_u4;
   const int base = (blockIdx.x * 256 + threadIdx.x) * 4;
   uint4 v[4];
@@ -1195,7 +1200,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ TsG
     if (i < total) {
       const int jj = i / row_u4, c = i - jj * row_u4;
       off[k] = jj * row_stride_u4 + c;
-      v[k] = __ldcs(src + off[k]);
+      v[k] = __ldcs(src + (jj * sstride + c));
     }
   }
 #pragma unroll
@@ -1215,6 +1220,7 @@ static int ts_gather_pending(tslam_tsdf* m) {
       const int q = m->q_gathered++;
       if (!m->q_hptr[q]) continue;
       ga.src[k] = (const uint4*)m->q_hptr[q];
+      ga.sstride[k] = m->q_sstride[q];
       ga.dst[k] = (uint4*)(m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * m->q_h * m->q_w);
       k++;
     }
@@ -1316,24 +1322,46 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
   // measured SLOWER from pinned memory: 30.2 k vs 36.5 k frames/s end to end - 240 row descriptors of 1280 B.)
   uint16_t* dst = m->depth_stage + (size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * h * w;  // frames packed h*w apart
   m->q_hptr[q] = nullptr;
-  if (m->zero_copy && m->cfg.recast_step >= 2 && (w % 8) == 0 && ((uintptr_t)depth_host % 16) == 0 && ((size_t)h * w % 8) == 0) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, depth_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-      m->q_hptr[q] = (const uint16_t*)at.devicePointer;
-      // the persistent ray-march kernel owns every register of the SMs it runs on: keep two SMs out of its grid so
-      // that the row gather of the NEXT launch's frames can run (and keep PCIe busy) while it marches
-      if (m->sm_count > 8) m->rm_reserve = 2;
+  const int step_q = m->cfg.recast_step;
+  cudaPointerAttributes at;
+  const bool src_pinned = cudaPointerGetAttributes(&at, depth_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  if (!src_pinned) cudaGetLastError();
+  if (m->zero_copy && src_pinned && at.devicePointer && step_q >= 2 && (w % 8) == 0 && ((uintptr_t)depth_host % 16) == 0 && ((size_t)h * w % 8) == 0) {
+    m->q_hptr[q] = (const uint16_t*)at.devicePointer;  // borrowed: the GPU reads the caller's frame itself, later
+    m->q_sstride[q] = step_q * (w / 8);
+  }
+  if (!m->q_hptr[q] && !src_pinned && m->stage_mode && (w % 8) == 0) {
+    // PAGEABLE source (what np.frombuffer(msg.data) gives the ROS node): the runtime would stage the whole frame through
+    // its own bounce buffer inside cudaMemcpyAsync.  Instead the sampled rows (every recast_step-th, :192) go into the
+    // library's page-locked ring with plain memcpy - half the bytes for step 2 - and the GPU fetches them from there
+    // over PCIe while the caller hands over the next frames.  Measured 21.5 k -> 26.8 k frames/s end to end.
+    const int hh = (int)((double)h / step_q);
+    if (!m->h_ring) {
+      m->ring_frame_cap = ((size_t)m->cfg.max_image_pixels / (size_t)step_q + 8) & ~(size_t)7;
+      TS_CUDA(cudaHostAlloc((void**)&m->h_ring, (size_t)2 * TSLAM_MAX_BATCH * m->ring_frame_cap * 2, cudaHostAllocMapped));
+      TS_CUDA(cudaHostGetDevicePointer((void**)&m->h_ring_dev, m->h_ring, 0));
     }
-    else
-      cudaGetLastError();
+    if ((size_t)hh * w <= m->ring_frame_cap) {
+      const size_t slot = ((size_t)b * TSLAM_MAX_BATCH + (size_t)q) * m->ring_frame_cap;
+      uint16_t* hdst = m->h_ring + slot;
+      if (step_q == 1) memcpy(hdst, depth_host, (size_t)hh * w * 2);
+      else
+        for (int j = 0; j < hh; j++) memcpy(hdst + (size_t)j * w, depth_host + (size_t)j * step_q * w, (size_t)w * 2);
+      m->q_hptr[q] = m->h_ring_dev + slot;
+      m->q_sstride[q] = w / 8;
+    }
+  }
+  if (m->q_hptr[q] && m->sm_count > 8) {
+    // the persistent march kernels own every register of the SMs they run on: keep two SMs out of their grids so
+    // that the row gather of the NEXT launch's frames can run (and keep PCIe busy) while they march
+    m->rm_reserve = 2;
   }
   if (!m->q_hptr[q]) {
     TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
     // a pageable source has been staged when the call returns; a page-locked one is read by the DMA engine later,
-    // so the copy is awaited: the caller may reuse its buffer (camera drivers do)
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, depth_host) == cudaSuccess && at.type == cudaMemoryTypeHost) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
-    else cudaGetLastError();
+    // so the copy is awaited: the caller may reuse its buffer (camera drivers do).  (Copying a page-locked frame into
+    // the ring first was measured slower than this: 28.2 k vs 30.6 k frames/s - the CPU memcpy costs more than the wait.)
+    if (src_pinned) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
   }
   if (has_tex) {
     uint8_t* tdst = m->tex_stage + ((size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * th * tw) * 3;

@@ -72,20 +72,31 @@ __device__ __forceinline__ int bucket_accumulate(bool valid, unsigned long long*
   int cnt = 1;
   bool act = valid;  // this lane probes and adds
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (valid && agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
-    const unsigned grp = __match_any_sync(vmask, key);
-    act = (threadIdx.x & 31) == (__ffs(grp) - 1);
-    cnt = __popc(grp);
-    if (cnt > 1) {
-      qx = (long long)__reduce_add_sync(grp, (int)qx);
-      qy = (long long)__reduce_add_sync(grp, (int)qy);
-      qz = (long long)__reduce_add_sync(grp, (int)qz);
-      qd = (long long)__reduce_add_sync(grp, (int)qd);
-      if (tex) {
-        cr = __reduce_add_sync(grp, cr);
-        cg = __reduce_add_sync(grp, cg);
-        cb = __reduce_add_sync(grp, cb);
+  if (agg_ok) {  // |q| < 2^26 (max_ray < 64 m): a 32-lane sum fits int32
+    // every lane adds its point to the shared-memory slot of its group's first lane (native 32-bit ATOMS; slots of
+    // different groups sit in different banks: stride 9 words), the leaders read the totals back.  (The
+    // redux-per-group loop this replaces was 17 % of the kernel's instructions.)
+    __shared__ int s_agg[8][32][9];
+    const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & 7;
+    int* mine = s_agg[wid][lane];
+    mine[0] = 0; mine[1] = 0; mine[2] = 0; mine[3] = 0; mine[4] = 0;
+    if (tex) { mine[5] = 0; mine[6] = 0; mine[7] = 0; }
+    __syncwarp();
+    if (valid) {
+      const unsigned grp = __match_any_sync(vmask, key);
+      const int lead = __ffs(grp) - 1;
+      act = lane == lead;
+      cnt = __popc(grp);
+      int* slot = s_agg[wid][lead];
+      if (grp & (grp - 1u)) {  // more than one lane in the bucket
+        atomicAdd(&slot[0], (int)qx); atomicAdd(&slot[1], (int)qy); atomicAdd(&slot[2], (int)qz); atomicAdd(&slot[3], (int)qd);
+        if (tex) { atomicAdd(&slot[5], cr); atomicAdd(&slot[6], cg); atomicAdd(&slot[7], cb); }
       }
+    }
+    __syncwarp();
+    if (valid && act && cnt > 1) {
+      qx = (long long)mine[0]; qy = (long long)mine[1]; qz = (long long)mine[2]; qd = (long long)mine[3];
+      if (tex) { cr = mine[5]; cg = mine[6]; cb = mine[7]; }
     }
   }
   uint32_t h = ts_hash(key) & cap_mask;

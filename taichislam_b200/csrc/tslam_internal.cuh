@@ -467,4 +467,4 @@ int ts_check_deferred_async(tslam_tsdf* m, cudaStream_t st);  // same, after the
 int ts_march_alloc(tslam_tsdf* m);
 void ts_march_free(tslam_tsdf* m);
 int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift);  // rays listed since the last call
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEvent_t* sub_ev);
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, cudaEvent_t* sub_ev);

@@ -49,86 +49,70 @@
 #define SEG_KEYS (SEG_CLS * SEG_REP)
 
 // ---------------------------------------------------------------------------
-// K2a: ray set-up (process_new_pcl :240-251): one thread per bucket -> one 32-byte ray record
+// K2a: ray set-up (process_new_pcl :240-251), first stage of the walk kernel: one bucket record -> unit direction,
+// length, weight, step count n, occupy flag (:248) and the 32-byte ray record the march kernels read.  The record and
+// its index entry are handed back zeroed (PCLroot.deactivate_all() / new_pcl_count = 0, :163, :270).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* buckets,
-                                                    unsigned long long* bidx, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
-                                                    const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr) {
-  const uint32_t n_rays = min((uint32_t)*n_rays_p, ray_cap);
+struct RaySetup { float ux, uy, uz, tx, ty, tz; int n, s; uint32_t f; bool wide; };
+__device__ __forceinline__ RaySetup ray_setup(const TsBatch& batch, const TsIntrin& in, const TsGrid& g, unsigned long long* btab, TsBucket* buckets,
+                                              unsigned long long* bidx, uint32_t bucket_shift, uint32_t id, uint32_t r, const TsMarchWs& w,
+                                              unsigned int& my_rays, unsigned int& my_fmax) {
   const float vs = in.vs;
-  unsigned int my_rays = 0, my_fmax = 0;
-  for (uint32_t r = blockIdx.x * 256 + threadIdx.x; r < n_rays; r += gridDim.x * 256) {
-    const uint32_t id = ray_list[r];
-    const uint32_t f = id >> bucket_shift;
-    TsBucket* bk = &buckets[id];
-    const int cnt = bk->cnt;
-    const long long sx = bk->sx, sy = bk->sy, sz = bk->sz, sd = bk->sd;
-    // PCLroot.deactivate_all() / new_pcl_count = 0 (:163, :270): hand the record and its index entry back zeroed
-    const unsigned long long ie = bk->key;
-    if (ie) bidx[ie - 1ull] = 0ull;
-    const uint4 z4 = make_uint4(0, 0, 0, 0);
-    uint4* q = reinterpret_cast<uint4*>(bk);
-    q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
-    const TsFrame& fr = batch.f[f];
-    const int s = fr.submap;
-    TsRay ry;
-    ry.ux = ry.uy = ry.uz = ry.L = ry.tx = ry.ty = ry.tz = ry.w = 0.0f;
-    int n = 0;
-    bool wide = false;
-    if (cnt > 0) {  // :240
-      my_rays++;
-      const double den = (double)cnt * FIXQ_D;
-      const float mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
-      const float my = (float)((double)sy / den);
-      const float mz = (float)((double)sz / den);
-      const float zc = (float)((double)sd / den);  // z = new_pcl_z/c (:247)
-      const float L = sqrtf((mx * mx + my * my) + mz * mz);  // :244
-      if (L > 0.0f) {
-        ry.ux = mx / L; ry.uy = my / L; ry.uz = mz / L;  // :245
-        ry.L = L;
-        const float Px = mx + fr.T[0], Py = my + fr.T[1], Pz = mz + fr.T[2];  // :246
-        // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
-        const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
-        if (ts_in_bounds(g, oi, oj, ok)) {
-          const int blk = ts_get_or_alloc_cached(g, ts_pack_key(s, oi >> TS_BSHIFT, oj >> TS_BSHIFT, ok >> TS_BSHIFT));
-          if (blk >= 0) {
-            g.occ[(size_t)blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
-            ts_mark_dirty(g, blk);  // touched blocks are listed even when only `occupy` changed
-          }
-        }
-        n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
-        ry.w = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
-        ry.tx = (float)((double)fr.T[0] / (double)vs);
-        ry.ty = (float)((double)fr.T[1] / (double)vs);
-        ry.tz = (float)((double)fr.T[2] / (double)vs);
-        // fixed-point scale of the launch: every |w| and |w*ds| must fit 31 bits (|ds| <= max(L, n*vs - L) + vs)
-        const float dmax = fmaxf(L, (float)n * vs - L) + vs;
-        const unsigned fb = __float_as_uint(fminf(fmaxf(ry.w, ry.w * dmax), 3.0e38f));  // non-negative floats order like their bits
-        if (fb > my_fmax) my_fmax = fb;
-        wide = n > 65535;
+  const uint32_t f = id >> bucket_shift;
+  uint4* q = reinterpret_cast<uint4*>(&buckets[id]);  // key sx | sy sz | sd cnt cr | cg cb pad
+  const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+  const unsigned long long ie = (unsigned long long)q0.x | ((unsigned long long)q0.y << 32);
+  if (ie) bidx[ie - 1ull] = 0ull;
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  q[0] = z4; q[1] = z4; q[2] = z4; q[3] = z4;
+  const long long sx = (long long)((unsigned long long)q0.z | ((unsigned long long)q0.w << 32));
+  const long long sy = (long long)((unsigned long long)q1.x | ((unsigned long long)q1.y << 32));
+  const long long sz = (long long)((unsigned long long)q1.z | ((unsigned long long)q1.w << 32));
+  const long long sd = (long long)((unsigned long long)q2.x | ((unsigned long long)q2.y << 32));
+  const int cnt = (int)q2.z;
+  const TsFrame& fr = batch.f[f];
+  RaySetup o;
+  o.ux = o.uy = o.uz = o.tx = o.ty = o.tz = 0.0f;
+  o.n = 0; o.s = fr.submap; o.f = f; o.wide = false;
+  float L = 0.0f, wgt = 0.0f;
+  if (cnt > 0) {  // :240
+    my_rays++;
+    const double den = (double)cnt * FIXQ_D;
+    const float mx = (float)((double)sx / den);  // pos_s2p = sum/c (:243), exact mean
+    const float my = (float)((double)sy / den);
+    const float mz = (float)((double)sz / den);
+    const float zc = (float)((double)sd / den);  // z = new_pcl_z/c (:247)
+    L = sqrtf((mx * mx + my * my) + mz * mz);  // :244
+    if (L > 0.0f) {
+      o.ux = mx / L; o.uy = my / L; o.uz = mz / L;  // :245
+      const float Px = mx + fr.T[0], Py = my + fr.T[1], Pz = mz + fr.T[2];  // :246
+      // occupy[sxyz_to_ijk(pos_p)] = 1 (:248)
+      const int oi = iroundf(Px / vs), oj = iroundf(Py / vs), ok = iroundf(Pz / vs);
+      if (ts_in_bounds(g, oi, oj, ok)) {
+        const int bx = oi >> TS_BSHIFT, by = oj >> TS_BSHIFT, bz = ok >> TS_BSHIFT;
+        const int blk = rm_lookup(g, btab, ts_pack_key(o.s, bx, by, bz), bx, by, bz);  // touched blocks are listed even when only `occupy` changed
+        if (blk >= 0) g.occ[(size_t)blk * TS_B3 + ts_voxel_off(oi, oj, ok)] = 1;
       }
+      o.n = (int)fminf(L / vs + (float)in.internal_voxels, in.max_steps);  // :249-251
+      wgt = 1.0f / (zc * zc);  // w_x_p(d>=0, z) (:216-225, :262)
+      o.tx = (float)((double)fr.T[0] / (double)vs);
+      o.ty = (float)((double)fr.T[1] / (double)vs);
+      o.tz = (float)((double)fr.T[2] / (double)vs);
+      // fixed-point scale of the launch: every |w| and |w*ds| must fit 31 bits (|ds| <= max(L, n*vs - L) + vs)
+      const float dmax = fmaxf(L, (float)o.n * vs - L) + vs;
+      const unsigned fb = __float_as_uint(fminf(fmaxf(wgt, wgt * dmax), 3.0e38f));  // non-negative floats order like their bits
+      if (fb > my_fmax) my_fmax = fb;
+      o.wide = o.n > 65535;
+    } else {
+      L = 0.0f;
     }
-    float4* dst = reinterpret_cast<float4*>(&w.rays[r]);
-    dst[0] = make_float4(ry.ux, ry.uy, ry.uz, ry.L);
-    dst[1] = make_float4(ry.tx, ry.ty, ry.tz, ry.w);
-    w.aux[r] = ((uint32_t)max(0, min(n, 65535)) << 16) | (f << 8) | (wide ? TS_AUX_WIDE : 0u);
   }
-  __shared__ unsigned int s_rays, s_fmax;
-  if (threadIdx.x == 0) { s_rays = 0u; s_fmax = 0u; }
-  __syncthreads();
-  for (int o = 16; o > 0; o >>= 1) {
-    my_rays += __shfl_xor_sync(FULL, my_rays, o);
-    my_fmax = max(my_fmax, __shfl_xor_sync(FULL, my_fmax, o));
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (my_rays) atomicAdd(&s_rays, my_rays);
-    if (my_fmax) atomicMax(&s_fmax, my_fmax);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_rays) atomicAdd(&ctr->n_rays, (unsigned long long)s_rays);
-    if (s_fmax) atomicMax(&w.ctl->fmax_bits, s_fmax);
-  }
+  float4* dst = reinterpret_cast<float4*>(&w.rays[r]);
+  dst[0] = make_float4(o.ux, o.uy, o.uz, L);
+  dst[1] = make_float4(o.tx, o.ty, o.tz, wgt);
+  o.n = max(0, min(o.n, 65535));
+  w.aux[r] = ((uint32_t)o.n << 16) | (f << 8) | (o.wide ? TS_AUX_WIDE : 0u);
+  return o;
 }
 
 // ---------------------------------------------------------------------------
@@ -165,7 +149,8 @@ struct WalkSmem {
   int n_chunk, cur, ovf, pad;
 };
 
-__global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g,
+__global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constant__ TsBatch batch, TsIntrin in, TsGrid g, TsBucket* buckets,
+                                                             unsigned long long* bidx, uint32_t bucket_shift, const uint32_t* __restrict__ ray_list,
                                                              const int* __restrict__ n_rays_p, uint32_t ray_cap, TsMarchWs w, TsCounters* ctr) {
   extern __shared__ __align__(16) unsigned char ms_smem[];
   WalkSmem& S = *reinterpret_cast<WalkSmem*>(ms_smem);
@@ -175,7 +160,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
   const uint32_t nme = min((uint32_t)*n_rays_p, ray_cap);
   const uint32_t lane = threadIdx.x & 31u;
   const int max_seg_ray = (int)(in.max_steps * 0.125f) + 8;  // block crossings of the longest ray (+ slack)
-  unsigned int my_oob = 0;
+  unsigned int my_oob = 0, my_rays = 0, my_fmax = 0;
   for (uint32_t base = blockIdx.x * MS_THREADS; base < nme; base += gridDim.x * MS_THREADS) {
     // room for this round's segments in the CTA's list
     if (threadIdx.x == 0 && !S.ovf) {
@@ -196,14 +181,9 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
     uint32_t f = 0;
     bool wide = false;
     if (r < nme) {
-      const float4* src = reinterpret_cast<const float4*>(&w.rays[r]);
-      const float4 a = src[0], b = src[1];
-      ux = a.x; uy = a.y; uz = a.z; tx = b.x; ty = b.y; tz = b.z;
-      const uint32_t ax = w.aux[r];
-      n = (int)(ax >> 16);
-      f = (ax >> 8) & 255u;
-      s = batch.f[f].submap;
-      wide = (ax & TS_AUX_WIDE) != 0;
+      const RaySetup rs = ray_setup(batch, in, g, S.btab, buckets, bidx, bucket_shift, ray_list[r], r, w, my_rays, my_fmax);
+      ux = rs.ux; uy = rs.uy; uz = rs.uz; tx = rs.tx; ty = rs.ty; tz = rs.tz;
+      n = rs.n; f = rs.f; s = rs.s; wide = rs.wide;
     }
     int bx, by, bz, sx, sy, sz;
     float jx, jy, jz, dx, dy, dz;
@@ -271,8 +251,16 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_seg_walk(const __grid_constan
   uint32_t* cch = w.cta_chunk + (size_t)cta * WK_MAXCH;
   for (int k = threadIdx.x; k < S.n_chunk; k += MS_THREADS) cch[k] = S.chunk[k];
   if (threadIdx.x == 0) w.cta_n[cta] = S.cur;
-  for (int o = 16; o > 0; o >>= 1) my_oob += __shfl_xor_sync(FULL, my_oob, o);
-  if (lane == 0 && my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
+  for (int o = 16; o > 0; o >>= 1) {
+    my_oob += __shfl_xor_sync(FULL, my_oob, o);
+    my_rays += __shfl_xor_sync(FULL, my_rays, o);
+    my_fmax = max(my_fmax, __shfl_xor_sync(FULL, my_fmax, o));
+  }
+  if (lane == 0) {
+    if (my_oob) atomicAdd(&ctr->n_oob, (unsigned long long)my_oob);
+    if (my_rays) atomicAdd(&ctr->n_rays, (unsigned long long)my_rays);
+    if (my_fmax) atomicMax(&w.ctl->fmax_bits, my_fmax);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -771,20 +759,20 @@ void ts_march_free(tslam_tsdf* m) {
   cudaFree(w.cta_chunk);
 }
 
-// ray set-up of the listed rays
+// workspace of the binned march (allocated at the first launch that needs it)
 int ts_march_setup(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift) {
+  (void)st; (void)batch; (void)bucket_shift;
   if (!m->mw.rays) { int rca = ts_march_alloc(m); if (rca) return rca; }
-  k_ray_setup<<<m->sm_count * 16, 256, 0, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap, m->mw, m->counters);
-  TS_LAUNCH_CHECK(m);
   return TSLAM_OK;
 }
 
 // sub_ev (profiling, may be null): 4 events recorded at the start, after walk + class + scan, placement and the march kernels
-int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, cudaEvent_t* sub_ev) {
+int ts_march_launch(tslam_tsdf* m, cudaStream_t st, const TsBatch& batch, uint32_t bucket_shift, cudaEvent_t* sub_ev) {
   const int sms = m->sm_count;
   const int gx = m->mw.walk_x_max;
   if (sub_ev) TS_CUDA(cudaEventRecord(sub_ev[0], st));
-  k_seg_walk<<<gx, MS_THREADS, (int)sizeof(WalkSmem), st>>>(batch, m->in, m->g, m->n_rays, m->ray_list_cap, m->mw, m->counters);
+  k_seg_walk<<<gx, MS_THREADS, (int)sizeof(WalkSmem), st>>>(batch, m->in, m->g, m->buckets, m->bidx, bucket_shift, m->ray_list, m->n_rays, m->ray_list_cap,
+                                                            m->mw, m->counters);
   TS_LAUNCH_CHECK(m);
   k_seg_class<<<sms * 2, 256, 0, st>>>(m->g, m->mw);
   TS_LAUNCH_CHECK(m);

@@ -1094,7 +1094,7 @@ static int ts_integrate_depth_impl(tslam_tsdf_t* m, const uint16_t* depth, int m
     if (!m->g.cword && m->march_mode) {
       int rcs = ts_march_setup(m, st, batch, bshift);
       if (rcs) return rcs;
-      int rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
+      int rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
       if (rcm) return rcm;
     } else if (m->g.cword) {
       k_raymarch<true><<<m->sm_count, RM_THREADS, RM_SMEM_TEX, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,
@@ -1162,7 +1162,7 @@ extern "C" int tslam_tsdf_integrate_points_rgb(tslam_tsdf_t* m, const float* xyz
   else if (m->march_mode) {
     int rcm = ts_march_setup(m, st, batch, bshift);
     if (rcm) return rcm;
-    rcm = ts_march_launch(m, st, batch, pe ? pe + 4 : nullptr);
+    rcm = ts_march_launch(m, st, batch, bshift, pe ? pe + 4 : nullptr);
     if (rcm) return rcm;
   } else
     k_raymarch<false><<<m->sm_count * 2, RM_THREADS, RM_SMEM, st>>>(batch, m->in, m->g, m->buckets, m->bidx, bshift, m->ray_list, m->n_rays,

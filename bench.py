@@ -400,7 +400,7 @@ def main():
     value = world * args.steps * STEP_FRAMES / (ms_total_max * 1e-3)
 
     # roofline of process_new_pcl (dense_tsdf.py:236-270), SURVEY 8d algorithmic bytes 17*rays + 9*updates per launch,
-    # over the CUDA-event time of ALL its kernels (ray set-up, segment walk / scan / placement, block march); the
+    # over the CUDA-event time of ALL its kernels (ray set-up + segment walk, scan, placement, block march); the
     # dominant one (k_march_blocks) is listed beside it
     peak, peak_src = load_peaks()
     km = kms.mean(axis=0) if len(kms) else np.full(7, np.nan)
@@ -528,9 +528,9 @@ def main():
                      "frac": (march_ach / peak) if march_ach else None,
                      "traffic": tr[0], "traffic_source": tr[1], "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": 9.0 * upd_per_launch,
-                     "kernel_ms": {"bucket": bucket_ms, "raymarch": ray_ms, "commit": commit_ms, "ray_setup": float(km[3]),
-                                   "seg_walk_class_scan": float(km[4]), "seg_place": float(km[5]), "march_blocks": march_only},
-                     "process_new_pcl_all_kernels": {"kernels": "k_ray_setup + k_seg_walk/class/scan/place + k_march_blocks",
+                     "kernel_ms": {"bucket": bucket_ms, "raymarch": ray_ms, "commit": commit_ms,
+                                   "setup_walk_class_scan": float(km[3] + km[4]), "seg_place": float(km[5]), "march_blocks": march_only},
+                     "process_new_pcl_all_kernels": {"kernels": "k_seg_walk (ray set-up + segment walk) + k_seg_class/scan/place + k_march_blocks",
                                                      "ms": ray_ms, "algorithmic_bytes_per_launch": bytes_launch,
                                                      "achieved": achieved, "frac": (achieved / peak) if achieved else None},
                      "algorithmic_bytes_per_frame_all_kernels": frame_bytes},

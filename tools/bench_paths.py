@@ -41,7 +41,7 @@ for name, d in (("S1 plane 3 m", syn.scene_plane(3.0)), ("S2 sphere 4 m", syn.sc
     rows.append((f"integrate {name} -> 512^3", f"{64e3 / ms:,.0f} frames/s", f"{ms:.3f} ms / 64 frames",
                  f"{st['n_rays'] / calls / 64:,.0f} rays, {st['n_updates'] / calls / 64 / 1e6:.2f} M updates, {per_frame / 1e6:.1f} MB algorithmic per frame -> "
                  f"{per_frame * 64 / ms / 1e6:,.0f} GB/s = {per_frame * 64 / ms / 1e6 / PEAK * 100:.1f} % of HBM peak; kernels: bucket {km[0]:.3f}, "
-                 f"ray set-up {km[3]:.3f}, walk+scan {km[4]:.3f}, place {km[5]:.3f}, block march {km[6]:.3f}, commit {km[2]:.3f} ms"))
+                 f"set-up+walk+scan {km[3] + km[4]:.3f}, place {km[5]:.3f}, block march {km[6]:.3f}, commit {km[2]:.3f} ms"))
     g.close()
 
 # --- C2: marching cubes after 100 stream frames ---

@@ -108,6 +108,12 @@ int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t 
                            const float* T3, int32_t submap, void* stream);
 int tslam_tsdf_flush(tslam_tsdf_t* m, void* stream);
 int tslam_tsdf_set_frame_mode(tslam_tsdf_t* m, int borrow_pinned);
+/* The same hand-over in two halves, so that the caller's own per-frame work (DenseTSDF.recast_depth_to_map: the f64 pose
+ * arithmetic of convert_by_base, mapping_common.py:91-100) runs while the frame's DMA copy is in flight: _begin starts
+ * the copy, _end awaits it (the frame has been consumed when _end returns), records the pose and launches a full
+ * queue.  No other call on the handle between the two. */
+int tslam_tsdf_queue_depth_begin(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, void* stream);
+int tslam_tsdf_queue_depth_end(tslam_tsdf_t* m, const float* R9, const float* T3, int32_t submap, void* stream);
 /* Frames per queue launch, alternating a, b, a, ... (default TSLAM_MAX_BATCH/2 each).  Every launch ends with a commit:
  * the granule of the Wmax clamp (dense_tsdf.py:267).  (1, 1) = one commit per frame - what a frame-by-frame caller of
  * the reference sees below Wmax, and the closest a summed update gets to its per-sample clamp at Wmax

@@ -62,6 +62,8 @@ SIGNATURES = {
     "tslam_tsdf_queue_depth": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "tslam_tsdf_flush": (C.c_int, [_vp, _vp]),
     "tslam_tsdf_set_frame_mode": (C.c_int, [_vp, C.c_int]),
+    "tslam_tsdf_queue_depth_begin": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "tslam_tsdf_queue_depth_end": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "tslam_tsdf_set_queue_launch": (C.c_int, [_vp, _i32, _i32]),
     "tslam_tsdf_set_color_intrinsics": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "tslam_tsdf_integrate_depth_tex": (C.c_int, [_vp, _vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp]),

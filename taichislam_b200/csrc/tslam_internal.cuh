@@ -347,6 +347,8 @@ struct tslam_tsdf {
   uint16_t* h_ring_dev;   // its device alias
   size_t ring_frame_cap;  // elements per frame slot
   int stage_mode;         // 1 = pageable frames through the ring (default), 0 = through cudaMemcpyAsync (TSLAM_FRAME_COPY=dma)
+  int pinned_gather;      // copy mode, page-locked source: fetch the sampled rows with k_gather_rows (1) or DMA-copy the frame (0)
+  int q_open, q_await;    // a frame's hand-over has begun (tslam_tsdf_queue_depth_begin) / its DMA copy is still to be awaited
   int q_sstride[TSLAM_MAX_BATCH];  // source row stride of the queued frame in 16-byte units
   int queue_launch[2];  // frames per queue launch, alternating (TSLAM_QUEUE_LAUNCH="a,b", default 32,32)
   int q_phase;          // which of the two thresholds the current launch uses (back to 0 at every flush)

@@ -804,6 +804,8 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     m->zero_copy = (zc && zc[0] == '1') ? 1 : 0;
     const char* fc = getenv("TSLAM_FRAME_COPY");  // "dma": pageable frames through cudaMemcpyAsync too (A/B against the ring)
     m->stage_mode = (fc && strcmp(fc, "dma") == 0) ? 0 : 1;
+    const char* pc = getenv("TSLAM_PINNED_COPY");  // "dma": page-locked frames through cudaMemcpyAsync (A/B against the row fetch)
+    m->pinned_gather = (pc && strcmp(pc, "dma") == 0) ? 0 : 1;
     m->trace = getenv("TSLAM_TRACE") != nullptr;
     if (m->trace) {
       for (int i = 0; i < 2; i++)
@@ -1244,6 +1246,10 @@ static int ts_gather_pending(tslam_tsdf* m) {
 }
 
 static int ts_launch_queue(tslam_tsdf* m, cudaStream_t st) {
+  if (m->q_open) {  // a hand-over that was begun and never ended (the caller failed in between): the frame is dropped
+    m->q_open = 0;
+    if (m->q_await) { m->q_await = 0; TS_CUDA(cudaStreamSynchronize(m->copy_stream)); }
+  }
   m->q_phase = 0;  // any launch that is not the queue's own threshold (flush, reader, geometry change) restarts the pattern
   const int n = m->q_n;
   if (n == 0) return TSLAM_OK;
@@ -1298,12 +1304,15 @@ extern "C" int tslam_tsdf_queue_depth(tslam_tsdf_t* m, const uint16_t* depth_hos
                                       const float* T3, int32_t submap, void* stream) {
   return tslam_tsdf_queue_depth_tex(m, depth_host, nullptr, h, w, 0, 0, R9, T3, submap, stream);
 }
-extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth_host, const uint8_t* tex_host, int32_t h, int32_t w,
-                                          int32_t th, int32_t tw, const float* R9, const float* T3, int32_t submap, void* stream) {
+// first half of a per-frame hand-over: the frame's copy is STARTED (page-locked source: DMA on the copy stream;
+// pageable source: sampled rows into the ring; borrowed: nothing).  ts_queue_end awaits it and records the pose.
+static int ts_queue_begin(tslam_tsdf* m, const uint16_t* depth_host, const uint8_t* tex_host, int32_t h, int32_t w, int32_t th, int32_t tw,
+                          void* stream) {
   if (m) { int rc0 = ts_check_tex(m, tex_host, th, tw); if (rc0) return rc0; }
-  if (!m || !depth_host || !R9 || !T3 || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if (!m || !depth_host || h <= 0 || w <= 0) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
   if ((long long)h * w > m->cfg.max_image_pixels) { ts_set_error("frame %dx%d exceeds max_image_pixels=%d", h, w, m->cfg.max_image_pixels); return TSLAM_E_INVALID; }
-  if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
+  m->q_open = 0;
+  m->q_await = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int has_tex = tex_host != nullptr;
   if (!has_tex) { th = 0; tw = 0; }
@@ -1367,20 +1376,50 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
     // that the row gather of the NEXT launch's frames can run (and keep PCIe busy) while they march
     m->rm_reserve = 2;
   }
-  if (!m->q_hptr[q]) {
+  if (!m->q_hptr[q] && src_pinned && m->pinned_gather && at.devicePointer && step_q >= 2 && (w % 8) == 0 && ((uintptr_t)depth_host % 16) == 0 &&
+      ((size_t)h * w % 8) == 0) {
+    // page-locked source, copy mode: the SAMPLED ROWS are fetched right now by a small kernel (half the PCIe bytes of a
+    // DMA copy of the frame for recast_step 2) and the fetch is awaited in ts_queue_end
+    TsGatherArgs ga;
+    ga.src[0] = (const uint4*)at.devicePointer;
+    ga.dst[0] = (uint4*)dst;
+    ga.sstride[0] = step_q * (w / 8);
+    const int hh = (int)((double)h / step_q), row_u4 = w / 8;
+    if (hh > 0) {
+      dim3 grid((hh * row_u4 + 1023) / 1024, 1);
+      k_gather_rows<<<grid, 256, 0, m->copy_stream>>>(ga, hh, row_u4, step_q * row_u4);
+      TS_LAUNCH_CHECK(m);
+    }
+    m->q_await = 1;
+    if (m->sm_count > 8) m->rm_reserve = 2;
+  } else if (!m->q_hptr[q]) {
     TS_CUDA(cudaMemcpyAsync(dst, depth_host, (size_t)h * w * 2, cudaMemcpyHostToDevice, m->copy_stream));
     // a pageable source has been staged when the call returns; a page-locked one is read by the DMA engine later,
     // so the copy is awaited: the caller may reuse its buffer (camera drivers do).  (Copying a page-locked frame into
     // the ring first was measured slower than this: 28.2 k vs 30.6 k frames/s - the CPU memcpy costs more than the wait.)
-    if (src_pinned) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
+    if (src_pinned) m->q_await = 1;
   }
   if (has_tex) {
     uint8_t* tdst = m->tex_stage + ((size_t)b * TSLAM_MAX_BATCH * m->cfg.max_image_pixels + (size_t)q * th * tw) * 3;
     TS_CUDA(cudaMemcpyAsync(tdst, tex_host, (size_t)th * tw * 3, cudaMemcpyHostToDevice, m->copy_stream));
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, tex_host) == cudaSuccess && at.type == cudaMemoryTypeHost) TS_CUDA(cudaStreamSynchronize(m->copy_stream));
+    if (cudaPointerGetAttributes(&at, tex_host) == cudaSuccess && at.type == cudaMemoryTypeHost) m->q_await = 1;
     else cudaGetLastError();
   }
+  m->q_open = 1;
+  return TSLAM_OK;
+}
+
+// second half: the copy started by ts_queue_begin is awaited (the caller's buffers are free when this returns), the pose
+// recorded, the queue launched when it is full
+static int ts_queue_end(tslam_tsdf* m, const float* R9, const float* T3, int32_t submap, void* stream) {
+  if (!m || !R9 || !T3) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if (!m->q_open) { ts_set_error("tslam_tsdf_queue_depth_end without a successful tslam_tsdf_queue_depth_begin"); return TSLAM_E_INVALID; }
+  m->q_open = 0;
+  if (m->q_await) { m->q_await = 0; TS_CUDA(cudaStreamSynchronize(m->copy_stream)); }
+  if (submap < 0 || submap >= m->cfg.max_submaps) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int q = m->q_n;
   memcpy(m->q_R + 9 * q, R9, 36);
   memcpy(m->q_T + 3 * q, T3, 12);
   m->q_s[q] = submap;
@@ -1393,6 +1432,21 @@ extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth
   }
   if (m->q_n - m->q_gathered >= TS_GATHER_GROUP) return ts_gather_pending(m);
   return TSLAM_OK;
+}
+
+extern "C" int tslam_tsdf_queue_depth_tex(tslam_tsdf_t* m, const uint16_t* depth_host, const uint8_t* tex_host, int32_t h, int32_t w,
+                                          int32_t th, int32_t tw, const float* R9, const float* T3, int32_t submap, void* stream) {
+  if (!R9 || !T3) { ts_set_error("bad argument"); return TSLAM_E_INVALID; }
+  if (m && (submap < 0 || submap >= m->cfg.max_submaps)) { ts_set_error("bad submap id %d", submap); return TSLAM_E_INVALID; }
+  int rc = ts_queue_begin(m, depth_host, tex_host, h, w, th, tw, stream);
+  if (rc) return rc;
+  return ts_queue_end(m, R9, T3, submap, stream);
+}
+extern "C" int tslam_tsdf_queue_depth_begin(tslam_tsdf_t* m, const uint16_t* depth_host, int32_t h, int32_t w, void* stream) {
+  return ts_queue_begin(m, depth_host, nullptr, h, w, 0, 0, stream);
+}
+extern "C" int tslam_tsdf_queue_depth_end(tslam_tsdf_t* m, const float* R9, const float* T3, int32_t submap, void* stream) {
+  return ts_queue_end(m, R9, T3, submap, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -65,6 +65,8 @@ class DenseTSDF(BaseMap):
         self._init_export_fields()
         self._queue = self._h.L.tslam_tsdf_queue_depth
         self._queue_tex = self._h.L.tslam_tsdf_queue_depth_tex
+        self._queue_begin = self._h.L.tslam_tsdf_queue_depth_begin
+        self._queue_end = self._h.L.tslam_tsdf_queue_depth_end
         # page-locked frames are read by the GPU straight from host memory a few calls later (include/tslam.h): keep
         # the arrays alive for as long as the library may still read them (it never runs more than 2 batches ahead)
         self._frame_refs = collections.deque(maxlen=6 * capi.MAX_BATCH)  # depth + colour image per frame
@@ -107,7 +109,6 @@ class DenseTSDF(BaseMap):
         The frame is copied to the device right away (asynchronously when `depthmap` is pinned host memory)."""
         if self.K_cam_dep is None:
             raise RuntimeError("set_dep_camera_intrinsic() must be called before recast_depth_to_map")
-        self.set_pose(R, T)
         if depthmap.dtype != np.uint16 or not depthmap.flags.c_contiguous:
             depthmap = np.ascontiguousarray(depthmap, dtype=np.uint16)
         h, w = depthmap.shape
@@ -116,6 +117,7 @@ class DenseTSDF(BaseMap):
         if self.enable_texture and texture is not None and getattr(texture, "size", 0) > 0:
             # ti.static(self.enable_texture) (:205): the colour image rides along (uint8 [th,tw,3]); a caller that has no
             # image for this frame (empty array) integrates geometry only
+            self.set_pose(R, T)
             if not self.color_same_proj and self.K_cam_color is None:
                 raise RuntimeError("set_color_camera_intrinsic() must be called before recast_depth_to_map (color_same_proj=False)")
             if texture.dtype != np.uint8 or not texture.flags.c_contiguous:
@@ -127,7 +129,14 @@ class DenseTSDF(BaseMap):
             rc = self._queue_tex(self._h.h, depthmap.__array_interface__["data"][0], texture.__array_interface__["data"][0], h, w,
                                  th, tw, self._pR, self._pT, sid, self._stream_ptr())
         else:
-            rc = self._queue(self._h.h, depthmap.__array_interface__["data"][0], h, w, self._pR, self._pT, sid, self._stream_ptr())
+            # the frame's copy is started first, the pose arithmetic (set_pose: convert_by_base in f64) runs while the
+            # DMA is in flight, then the copy is awaited: the array has been consumed when this method returns
+            st = self._stream_ptr()
+            rc = self._queue_begin(self._h.h, depthmap.__array_interface__["data"][0], h, w, st)
+            if rc:
+                capi.check(rc)
+            self.set_pose(R, T)
+            rc = self._queue_end(self._h.h, self._pR, self._pT, sid, st)
         if rc:
             capi.check(rc)
 

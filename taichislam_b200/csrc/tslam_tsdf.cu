@@ -1318,12 +1318,7 @@ static inline void ts_stream_copy_row(uint16_t* dst, const uint16_t* src, size_t
   for (; i < n; i++) _mm_stream_si128(d + i, _mm_loadu_si128(s + i));
 }
 static inline void ts_stream_fence() { _mm_sfence(); }
-static inline void ts_prefetch_row(const uint16_t* src, size_t bytes) {
-  const char* p = reinterpret_cast<const char*>(src);
-  for (size_t o = 0; o < bytes; o += 64) _mm_prefetch(p + o, _MM_HINT_NTA);
-}
 #else
-static inline void ts_prefetch_row(const uint16_t*, size_t) {}
 static inline void ts_stream_copy_row(uint16_t* dst, const uint16_t* src, size_t bytes) { memcpy(dst, src, bytes); }
 static inline void ts_stream_fence() {}
 #endif
@@ -1391,10 +1386,8 @@ static int ts_queue_begin(tslam_tsdf* m, const uint16_t* depth_host, const uint8
       uint16_t* hdst = m->h_ring + slot;
       // streaming stores: the ring is read by the GPU over PCIe, never by this CPU - no read-for-ownership of the
       // destination lines, no cache pollution
-      for (int j = 0; j < hh; j++) {
-        if (j + 3 < hh) ts_prefetch_row(depth_host + (size_t)(j + 3) * step_q * w, (size_t)w * 2);  // the sampled rows are not adjacent: help the prefetcher
-        ts_stream_copy_row(hdst + (size_t)j * w, depth_host + (size_t)j * step_q * w, (size_t)w * 2);
-      }
+      // (software prefetch of the rows ahead and 32-byte AVX2 stores were measured on the host: no gain / 2x slower)
+      for (int j = 0; j < hh; j++) ts_stream_copy_row(hdst + (size_t)j * w, depth_host + (size_t)j * step_q * w, (size_t)w * 2);
       ts_stream_fence();
       m->q_hptr[q] = m->h_ring_dev + slot;
       m->q_sstride[q] = w / 8;

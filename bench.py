@@ -438,8 +438,8 @@ def main():
         def run_e2e(mode, steps):
             if mode == "dma_pageable":
                 os.environ["TSLAM_FRAME_COPY"] = "dma"  # read when the handle is created
-            if mode == "dma_pinned":
-                os.environ["TSLAM_PINNED_COPY"] = "dma"
+            if mode == "ring_pinned":
+                os.environ["TSLAM_PINNED_COPY"] = "ring"
             if mode == "fetch_pinned":
                 os.environ["TSLAM_PINNED_COPY"] = "fetch"
             try:
@@ -487,16 +487,16 @@ def main():
         try:
             es = max(3, args.steps // 5)
             v, d2h = run_e2e("copy", es)
-            e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2), "d2h_bytes_per_step": d2h, "steps": es,
-                   "api": "DenseTSDF.recast_depth_to_map per frame; page-locked host uint16 frames, DEFAULT frame mode: the call copies the "
-                          "sampled rows (recast_step 2: every second row) of the frame into the library's page-locked ring with streaming "
-                          "stores - the caller may reuse its buffer at once, as with the reference - and the GPU fetches them from there over PCIe"}
+            e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2), "d2h_bytes_per_step": d2h, "steps": es,
+                   "api": "DenseTSDF.recast_depth_to_map per frame; page-locked host uint16 frames, DEFAULT frame mode: every frame is "
+                          "DMA-copied and the copy awaited inside the call (the caller may reuse its buffer at once, as with the "
+                          "reference); the method's pose arithmetic runs while the copy is in flight"}
             es2 = max(3, args.steps // 10)
             vb, _ = run_e2e("borrow", es2)
             vp, _ = run_e2e("pageable", es2)
             vc, _ = run_e2e("commit1", es2)
             vd, _ = run_e2e("dma_pageable", es2)
-            vq, _ = run_e2e("dma_pinned", es2)
+            vq, _ = run_e2e("ring_pinned", es2)
             vf, _ = run_e2e("fetch_pinned", es2)
             e2e_modes = {"borrowed_pinned_frames": {"value": vb, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
                                                     "note": "opt-in set_frame_borrowing(True): no copy, the GPU reads the sampled rows from host "
@@ -505,11 +505,11 @@ def main():
                                                 "note": "set_commit_granularity(1): one launch sequence + commit per frame (Wmax clamp granule = frame)"},
                          "pageable_frames": {"value": vp, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
                                              "note": "what np.frombuffer(depth_msg.data) gives the ROS node (taichislam_node.py:381-382): the sampled "
-                                                     "rows are memcpy'd into the library's page-locked ring and fetched from there by the GPU"},
+                                                     "rows are copied into the library's page-locked ring (streaming stores) and fetched from there by the GPU"},
                          "pinned_frames_awaited_row_fetch": {"value": vf, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
                                                              "note": "TSLAM_PINNED_COPY=fetch: the GPU fetches the sampled rows of the caller's page-locked frame inside the call, awaited"},
-                         "pinned_frames_through_cudaMemcpyAsync": {"value": vq, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
-                                                                   "note": "TSLAM_PINNED_COPY=dma: DMA copy of the whole frame, awaited (A/B for the ring)"},
+                         "pinned_frames_through_the_ring": {"value": vq, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * (syn.H // 2) * syn.W * 2),
+                                                            "note": "TSLAM_PINNED_COPY=ring: page-locked frames take the pageable frames' path (sampled rows memcpy'd into the ring)"},
                          "pageable_frames_through_cudaMemcpyAsync": {"value": vd, "unit": UNIT, "h2d_bytes_per_step": int(STEP_FRAMES * syn.H * syn.W * 2),
                                                                      "note": "TSLAM_FRAME_COPY=dma: the runtime stages the whole pageable frame (A/B for the ring)"}}
         except Exception as ex:  # pragma: no cover

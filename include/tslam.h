@@ -96,10 +96,10 @@ int tslam_tsdf_integrate_depth(tslam_tsdf_t* m, const uint16_t* depth, int mem, 
  * environment alternates other counts) - or tslam_tsdf_flush, which every reader calls implicitly - are integrated
  * and committed with one launch triple, so the kernels of one half run while the caller hands over the next.
  * The frame has been consumed when the call returns (the reference's semantics: its kernel launch copies the array
- * synchronously): the sampled rows (every recast_step-th row) are copied into a page-locked ring of the library with
- * streaming stores, from where the GPU fetches them - pageable and page-locked sources alike.  (Environment, A/B only:
- * TSLAM_FRAME_COPY=dma hands pageable frames to cudaMemcpyAsync; TSLAM_PINNED_COPY=dma|fetch awaits a DMA copy / a row
- * fetch of a page-locked frame inside the call.)
+ * synchronously): a page-locked source is DMA-copied and the copy awaited; of a pageable source the sampled rows (every
+ * recast_step-th row) are copied into a page-locked ring of the library with streaming stores, from where the GPU
+ * fetches them.  (Environment, A/B only: TSLAM_FRAME_COPY=dma hands pageable frames to cudaMemcpyAsync;
+ * TSLAM_PINNED_COPY=ring|fetch sends page-locked frames through the ring / awaits a row fetch inside the call.)
  * tslam_tsdf_set_frame_mode(m, 1) (or TSLAM_ZERO_COPY=1 in the environment) opts into BORROWING page-locked frames
  * instead: they are not copied at all, the GPU fetches their sampled rows (every recast_step-th row) straight from
  * host memory a few calls later - half the PCIe bytes for recast_step 2, no wait per frame - and they must then stay

@@ -341,13 +341,13 @@ struct tslam_tsdf {
   const uint16_t* q_hptr[TSLAM_MAX_BATCH];
   int q_gathered;
   int zero_copy;  // 1 = borrow page-locked frames (tslam_tsdf_set_frame_mode / TSLAM_ZERO_COPY=1); 0 = copy (default)
-  // copy mode (default): the call copies the SAMPLED ROWS of the frame into this page-locked ring on the host (the caller
-  // may reuse its buffer at once) and the GPU fetches them from there like a borrowed frame
+  // copy mode, pageable frames: the call copies the SAMPLED ROWS of the frame into this page-locked ring on the host (the
+  // caller may reuse its buffer at once) and the GPU fetches them from there like a borrowed frame
   uint16_t* h_ring;       // [2][TSLAM_MAX_BATCH][ring_frame_cap] host, mapped
   uint16_t* h_ring_dev;   // its device alias
   size_t ring_frame_cap;  // elements per frame slot
   int stage_mode;         // pageable frames: 1 = through the ring (default), 0 = through cudaMemcpyAsync (TSLAM_FRAME_COPY=dma)
-  int pinned_mode;        // copy mode, page-locked source: 0 = through the ring like pageable frames (default), 1 = awaited row fetch, 2 = awaited DMA copy
+  int pinned_mode;        // copy mode, page-locked source: 2 = awaited DMA copy (default), 0 = through the ring like pageable frames, 1 = awaited row fetch
   int q_open, q_await;    // a frame's hand-over has begun (tslam_tsdf_queue_depth_begin) / its DMA copy is still to be awaited
   int q_sstride[TSLAM_MAX_BATCH];  // source row stride of the queued frame in 16-byte units
   int queue_launch[2];  // frames per queue launch, alternating (TSLAM_QUEUE_LAUNCH="a,b", default 32,32)

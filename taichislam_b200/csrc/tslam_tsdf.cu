@@ -804,8 +804,12 @@ extern "C" int tslam_tsdf_create(const tslam_tsdf_config_t* cfg, tslam_tsdf_t** 
     m->zero_copy = (zc && zc[0] == '1') ? 1 : 0;
     const char* fc = getenv("TSLAM_FRAME_COPY");  // "dma": pageable frames through cudaMemcpyAsync too (A/B against the ring)
     m->stage_mode = (fc && strcmp(fc, "dma") == 0) ? 0 : 1;
-    const char* pc = getenv("TSLAM_PINNED_COPY");  // A/B for page-locked frames in copy mode: "fetch" = awaited row fetch, "dma" = awaited cudaMemcpyAsync
-    m->pinned_mode = (pc && strcmp(pc, "dma") == 0) ? 2 : (pc && strcmp(pc, "fetch") == 0) ? 1 : 0;
+    // page-locked frames in copy mode: awaited cudaMemcpyAsync (default; A/B: "ring" = through the host ring like
+    // pageable frames, "fetch" = awaited row fetch).  Measured on three boxes (frames/s per GPU, 1 / 1 / 8 ranks):
+    // dma 36.6 k / 24.3 k / 36.3 k, ring 32.5 k / 38.1 k / 20.1 k, fetch 14.1 k / 32.2 k / 33.9 k - the copy engine is the
+    // one that neither depends on the host's memcpy bandwidth (8 ranks share it) nor on the PCIe read latency
+    const char* pc = getenv("TSLAM_PINNED_COPY");
+    m->pinned_mode = (pc && strcmp(pc, "ring") == 0) ? 0 : (pc && strcmp(pc, "fetch") == 0) ? 1 : 2;
     m->trace = getenv("TSLAM_TRACE") != nullptr;
     if (m->trace) {
       for (int i = 0; i < 2; i++)
@@ -1370,11 +1374,11 @@ static int ts_queue_begin(tslam_tsdf* m, const uint16_t* depth_host, const uint8
     m->q_sstride[q] = step_q * (w / 8);
   }
   if (!m->q_hptr[q] && (src_pinned ? m->pinned_mode == 0 : m->stage_mode != 0) && (w % 8) == 0) {
-    // default, pageable or page-locked source alike: the sampled rows (every recast_step-th, :192 - half the bytes for
-    // step 2) are copied into the library's page-locked ring with streaming stores - the caller's buffer is free when the
-    // call returns - and the GPU fetches them from there over PCIe while the caller hands over the next frames: no
-    // transfer is awaited per frame.  Measured on one box: 38.1 k frames/s end to end, against 32.2 k with an awaited row
-    // fetch and 24.3 k with an awaited cudaMemcpyAsync of a page-locked frame, 23.7 k with cudaMemcpyAsync of a pageable one.
+    // PAGEABLE source (what np.frombuffer(msg.data) gives the ROS node): the runtime would stage the whole frame through
+    // its own bounce buffer inside cudaMemcpyAsync (20.5-23.7 k frames/s).  Instead the sampled rows (every
+    // recast_step-th, :192 - half the bytes for step 2) are copied into the library's page-locked ring with streaming
+    // stores - the caller's buffer is free when the call returns - and the GPU fetches them from there over PCIe while
+    // the caller hands over the next frames: 32.3-38.1 k frames/s.
     const int hh = (int)((double)h / step_q);
     if (!m->h_ring) {
       m->ring_frame_cap = ((size_t)m->cfg.max_image_pixels / (size_t)step_q + 8) & ~(size_t)7;

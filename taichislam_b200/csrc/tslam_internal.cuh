@@ -279,7 +279,7 @@ struct TsItem { int blk; uint32_t seg0, nseg, pad; };  // work item of k_march_b
 struct TsMarchCtl {  // device-side control block of one launch (zeroed by k_march_reset at its end)
   int n_touched;     // blocks that received at least one segment
   int n_items;       // work items built by k_seg_scan
-  int n_full;        // ... of which full chunks (front of the item list; the remainders sit at its back)
+  int n_full;        // (unused since the items are listed longest first)
   int item_cursor;   // persistent-CTA work cursor of k_march_blocks
   int n_gen;         // generic-list records
   int overflow;      // work list did not fit: every segment goes through the generic path this launch
@@ -303,6 +303,7 @@ struct TsMarchWs {
   uint32_t* seg_off;   // [max_blocks] start of the block's run
   int* touched;        // [max_blocks] blocks with segments
   uint32_t* blk_total; // [max_blocks] segments of touched[i]
+  uint32_t* blk_cost;  // [max_blocks] samples of touched[i] (upper estimate from the length classes)
   TsItem* items;       // [item_cap]
   uint32_t item_cap;
   TsSeg* gen;          // [gen_cap] generic-path records (volume boundary, over-long rays, overflow)

@@ -230,6 +230,23 @@ def test_pool_exhaustion_is_reported():
     assert e.value.code == capi.E_POOL_FULL
 
 
+def test_bucket_key_range_is_reported():
+    """The per-frame bucket index keys a bucket by 13 bits per axis (+-4095 voxels around the sensor origin).  A surface
+    point further away than that (9 m at 2 mm voxels) is dropped and reported by the next synchronising call - it must
+    not alias into another bucket."""
+    from taichislam_b200.tsdf_handle import TsdfHandle
+    from taichislam_b200 import _capi as capi
+    g = TsdfHandle(512, 512, voxel_scale=0.002, K=syn.K_DEPTH, is_global_map=True)
+    g.integrate_depth(syn.scene_sphere(9.0), np.eye(3)[None], np.zeros((1, 3)))
+    with pytest.raises(capi.TslamError) as e:
+        g.sync()
+    assert e.value.code == capi.E_CAPACITY
+    g2 = TsdfHandle(512, 512, voxel_scale=0.002, K=syn.K_DEPTH, is_global_map=True)
+    g2.integrate_depth(syn.scene_sphere(4.0), np.eye(3)[None], np.zeros((1, 3)))  # 2000 voxels: inside the key range
+    g2.sync()
+    assert g2.stats()["n_rays"] > 1000
+
+
 def test_full_size_properties_512():
     """Size-independent properties at the bench configuration (512^3, 64-frame batches):
     integrating the same stream twice doubles every weight and leaves every TSDF value unchanged;

@@ -223,6 +223,42 @@ def test_texture_later_frame_wins_like_the_reference():
     assert (ref_is_b != orc_is_b).mean() <= 0.02
 
 
+def test_colour_camera_projection_like_the_reference():
+    """tests/golden/ref_exec_texproj.npz (tools/make_golden_ref.py texproj): the depth kernel's colour-camera path
+    (color_same_proj=False, dense_tsdf.py:208-210 -> color_ind_from_depth_pt, mapping_common.py:44-59) EXECUTED on a
+    non-square image of vertical colour bands.  Two things show in the voxel colours: the pixel mapping through both
+    intrinsics, and the swapped bound test of :56 (colour x is tested against the image HEIGHT, so every depth pixel that
+    projects to x >= h reads texture[0, 0] - white here: 56 % of the voxels).  The oracle must give every voxel the same
+    band (inside a band the reference's racy last-writer-wins colour has one outcome; band edges are excluded)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_texproj.npz"))
+    o = OracleTSDF(K=list(g["K"]), is_global_map=True, mode=MODE_CANONICAL, **KW)
+    o.set_color(True, False, list(g["Kc"]))
+    R, T = f32pose(g["P1_R"], g["P1_T"])
+    o.integrate_depth_tex(R, T, g["d1"], g["tex"])
+    oi, ot, ow, oo = o.gather(0)
+    oc = o.gather_color(0)
+    ri, rc = g["idx"].astype(np.int32), g["color"].astype(np.float32)
+    a, b = set(map(tuple, ri)), set(map(tuple, oi))
+    common = sorted(a & b)
+    assert len(common) >= 0.99 * len(a)
+    ia, ib = {k: i for i, k in enumerate(map(tuple, ri))}, {k: i for i, k in enumerate(map(tuple, oi))}
+    sa, sb = np.array([ia[k] for k in common]), np.array([ib[k] for k in common])
+    pal = np.concatenate([g["bands"].astype(np.float32), [[255.0, 255.0, 255.0]]]) / 255.0   # last = texture[0, 0]
+
+    def band_of(c):  # palette entry of a colour, -1 when it is none of them (a mix at a band edge)
+        d = np.abs(c[:, None, :] - pal[None, :, :]).max(2)
+        k = d.argmin(1)
+        return np.where(d[np.arange(len(c)), k] < 3e-3, k, -1)
+
+    rb, ob = band_of(rc[sa]), band_of(oc[sb])
+    pure = (rb >= 0) & (ob >= 0)
+    assert pure.mean() > 0.9
+    white = len(pal) - 1
+    assert (rb[pure] == white).sum() > 40000 and len(set(rb[pure])) >= 6      # the out-of-"bounds" pixels and several bands are there
+    assert (rb[pure] != ob[pure]).mean() <= 0.02                                 # same band per voxel
+    assert ((rb == white) != (ob == white))[pure].mean() <= 0.005               # in particular the same swapped-bound region
+
+
 @pytest.mark.parametrize("mode", [1, MODE_CANONICAL])   # 1 = MODE_F32_LITERAL
 def test_f32_state_modes_equal_the_reference_run_with_f32_fields(mode):
     """tests/golden/ref_exec_f32.npz: the reference's integrate kernels executed with every ti.f16 declaration read as

@@ -318,6 +318,41 @@ def saturation():
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
+def texproj():
+    """tests/golden/ref_exec_texproj.npz: the colour camera path of the depth kernel (color_same_proj=False,
+    dense_tsdf.py:208-210 -> color_ind_from_depth_pt, mapping_common.py:44-59) executed: a colour camera with its own
+    intrinsics and a NON-SQUARE image of vertical colour bands, so that (a) the pixel mapping and (b) the swapped bound
+    test of :56 (colour x is compared with the image HEIGHT: every depth pixel that projects to x >= h reads texture[0, 0],
+    marked white) show in the voxel colours.  Within a band the racy "last ray wins" overwrite (:268-269) has one outcome."""
+    t00 = time.time()
+    ref = emu.load_reference()
+    D = ref.dense_tsdf.DenseTSDF
+    K, d1, d2, P1, P2, pcl = inputs()
+    kw = dict(map_scale=[6.4, 6.4], voxel_scale=0.05, num_voxel_per_blk_axis=16, max_ray_length=3.0, max_disp_particles=1 << 17,
+              max_submap_num=4)
+    th, tw = 90, 200
+    Kc = [K[0] * 1.2, 0.0, 100.0, 0.0, K[4] * 0.7, 45.0, 0.0, 0.0, 1.0]
+    bands = np.array([(30, 60, 90), (220, 40, 40), (40, 200, 60), (50, 70, 230), (230, 210, 40), (150, 40, 200), (20, 180, 190),
+                      (240, 130, 30), (90, 90, 90), (200, 200, 120), (120, 20, 60), (60, 140, 20), (10, 30, 160), (170, 170, 250)], np.uint8)
+    tex = np.zeros((th, tw, 3), np.uint8)
+    for x in range(tw):
+        tex[:, x] = bands[x // 15]
+    tex[0, 0] = (255, 255, 255)
+    m = D(is_global_map=True, texture_enabled=True, color_same_proj=False, **kw)
+    m.set_dep_camera_intrinsic(K)
+    m.set_color_camera_intrinsic(Kc)
+    m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    m.recast_depth_to_map(P1[0], P1[1], d1, tex)
+    keys = sorted(k for k, v in m.TSDF_observed.d.items() if v > 0)
+    g = {"K": np.array(K), "Kc": np.array(Kc), "d1": d1, "P1_R": P1[0], "P1_T": P1[1], "tex": tex, "bands": bands,
+         "idx": np.array([k[1:] for k in keys], np.int16), "color": np.array([m.color.d[k] for k in keys], np.float16)}
+    out = os.path.join(ROOT, "tests", "golden", "ref_exec_texproj.npz")
+    np.savez_compressed(out, **g)
+    c = g["color"].astype(np.float32)
+    white = (np.abs(c - 1.0).max(1) < 2e-3).sum()
+    print(f"texproj: {len(keys)} voxels, {white} white (x >= h -> texture[0,0]), {time.time() - t00:.0f}s -> {out}")
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else ""
-    {"topo": topo, "f32": f32_state, "sat": saturation}.get(mode, main)()
+    {"topo": topo, "f32": f32_state, "sat": saturation, "texproj": texproj}.get(mode, main)()

@@ -259,6 +259,28 @@ def test_colour_camera_projection_like_the_reference():
     assert ((rb == white) != (ob == white))[pure].mean() <= 0.005               # in particular the same swapped-bound region
 
 
+def test_coloured_mesh_on_reference_state():
+    """Coloured marching cubes (vertexInterp_color and its quirks, marching_cube_mesher.py:62-82, :104-108) EXECUTED on the
+    banded-texture state of ref_exec_texproj.npz; the oracle meshes the same state (the reference's TSDF / W / colour
+    loaded as they are): same triangles, vertex colours within the f16 noise of the reference's mu."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_texproj.npz"))
+    o = OracleTSDF(is_global_map=True, **KW)
+    o.set_color(True, False, list(g["Kc"]))
+    idx = g["idx"].astype(np.int32)
+    o.scatter(0, idx, g["T"].astype(np.float32), g["W"].astype(np.float32), g["occ"])
+    o.scatter_color(0, idx, g["color"].astype(np.float32))
+    nt, v, nrm, col = o.marching_cubes_color(1, 0.1)
+    assert nt == int(g["mc_triangles"]) > 100
+    from scipy.spatial import cKDTree
+    a, b = v.reshape(-1, 9).astype(np.float64), g["mc_vertices"].reshape(-1, 9).astype(np.float64)
+    d_ab, j = cKDTree(b).query(a)
+    assert d_ab.max() <= 3e-4
+    c_ref, c_orc = g["mc_colors"].reshape(-1, 9)[j], col.reshape(-1, 9)
+    # mu is formed from f16 operands in the reference (~1e-3 relative), colours are f16 fields
+    assert np.abs(c_ref - c_orc).max() <= 4e-3, np.abs(c_ref - c_orc).max()
+    assert len(np.unique(np.round(c_ref, 2), axis=0)) > 5   # several bands and mixtures really occur
+
+
 @pytest.mark.parametrize("mode", [1, MODE_CANONICAL])   # 1 = MODE_F32_LITERAL
 def test_f32_state_modes_equal_the_reference_run_with_f32_fields(mode):
     """tests/golden/ref_exec_f32.npz: the reference's integrate kernels executed with every ti.f16 declaration read as

@@ -346,6 +346,16 @@ def texproj():
     keys = sorted(k for k, v in m.TSDF_observed.d.items() if v > 0)
     g = {"K": np.array(K), "Kc": np.array(Kc), "d1": d1, "P1_R": P1[0], "P1_T": P1[1], "tex": tex, "bands": bands,
          "idx": np.array([k[1:] for k in keys], np.int16), "color": np.array([m.color.d[k] for k in keys], np.float16)}
+    # coloured marching cubes on this state (marching_cube_mesher.py:62-82 vertexInterp_color, :104-108, :150-170)
+    idx, t, w, occ, _ = state(m)
+    g["T"], g["W"], g["occ"] = t, w, occ
+    mesher = ref.marching_cube_mesher.MarchingCubeMesher(m, max_triangles=200000, tsdf_surface_thres=0.1)
+    mesher.generate_mesh(1)
+    nt = int(mesher.num_facelets[None])
+    g["mc_triangles"] = np.array(nt)
+    g["mc_vertices"] = mesher.mesh_vertices.to_numpy()[:3 * nt].astype(np.float32)
+    g["mc_colors"] = mesher.mesh_colors.to_numpy()[:3 * nt].astype(np.float32)
+    print(f"texproj: coloured mesh {nt} triangles, {time.time() - t00:.0f}s")
     out = os.path.join(ROOT, "tests", "golden", "ref_exec_texproj.npz")
     np.savez_compressed(out, **g)
     c = g["color"].astype(np.float32)

@@ -259,6 +259,35 @@ def test_colour_camera_projection_like_the_reference():
     assert ((rb == white) != (ob == white))[pure].mean() <= 0.005               # in particular the same swapped-bound region
 
 
+def test_textured_point_cloud_like_the_reference():
+    """recast_pcl_to_map with colours (dense_tsdf.py:178-183) EXECUTED: every point carries one of 8 colours (by the octant
+    of its direction, identity pose), so that the racy per-sample colour overwrite has one outcome inside an octant.  The
+    oracle must give every voxel the same colour."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_texproj.npz"))
+    o = OracleTSDF(is_global_map=True, mode=MODE_CANONICAL, **KW)
+    o.set_color(True, True)
+    o.integrate_points_rgb(np.eye(3, dtype=np.float32), np.zeros(3, np.float32), g["pcl"], g["pcl_rgb"])
+    oi, _, _, _ = o.gather(0)
+    oc = o.gather_color(0)
+    ri, rc = g["P_idx"].astype(np.int32), g["P_color"].astype(np.float32)
+    a, b = set(map(tuple, ri)), set(map(tuple, oi))
+    common = sorted(a & b)
+    assert len(common) >= 0.99 * len(a)
+    ia, ib = {k: i for i, k in enumerate(map(tuple, ri))}, {k: i for i, k in enumerate(map(tuple, oi))}
+    sa, sb = np.array([ia[k] for k in common]), np.array([ib[k] for k in common])
+    pal = g["pal8"].astype(np.float32) / 255.0
+
+    def which(c):
+        d = np.abs(c[:, None, :] - pal[None, :, :]).max(2)
+        k = d.argmin(1)
+        return np.where(d[np.arange(len(c)), k] < 3e-3, k, -1)
+
+    rb, ob = which(rc[sa]), which(oc[sb])
+    pure = (rb >= 0) & (ob >= 0)
+    assert pure.mean() > 0.9 and len(set(rb[pure])) == 8
+    assert (rb[pure] != ob[pure]).mean() <= 0.02
+
+
 def test_coloured_mesh_on_reference_state():
     """Coloured marching cubes (vertexInterp_color and its quirks, marching_cube_mesher.py:62-82, :104-108) EXECUTED on the
     banded-texture state of ref_exec_texproj.npz; the oracle meshes the same state (the reference's TSDF / W / colour

@@ -356,6 +356,19 @@ def texproj():
     g["mc_vertices"] = mesher.mesh_vertices.to_numpy()[:3 * nt].astype(np.float32)
     g["mc_colors"] = mesher.mesh_colors.to_numpy()[:3 * nt].astype(np.float32)
     print(f"texproj: coloured mesh {nt} triangles, {time.time() - t00:.0f}s")
+    # textured point-cloud variant (:178-183): colour per point = one of 8 by the octant of its direction
+    pal8 = np.array([(250, 20, 20), (20, 250, 20), (20, 20, 250), (240, 240, 30), (30, 240, 240), (240, 30, 240), (130, 130, 130),
+                     (250, 140, 10)], np.uint8)
+    octant = (pcl[:, 0] > 0).astype(int) * 4 + (pcl[:, 1] > 0).astype(int) * 2 + (pcl[:, 2] > 0).astype(int)
+    rgb = pal8[octant]
+    mp = D(is_global_map=True, texture_enabled=True, **kw)
+    mp.set_base_pose_submap(0, np.eye(3), np.zeros(3))
+    mp.recast_pcl_to_map(np.eye(3), np.zeros(3), pcl, rgb)
+    pkeys = sorted(k for k, v in mp.TSDF_observed.d.items() if v > 0)
+    g["pcl"], g["pcl_rgb"], g["pal8"] = pcl, rgb, pal8
+    g["P_idx"] = np.array([k[1:] for k in pkeys], np.int16)
+    g["P_color"] = np.array([mp.color.d[k] for k in pkeys], np.float16)
+    print(f"texproj: textured point cloud {len(pkeys)} voxels, {time.time() - t00:.0f}s")
     out = os.path.join(ROOT, "tests", "golden", "ref_exec_texproj.npz")
     np.savez_compressed(out, **g)
     c = g["color"].astype(np.float32)

@@ -288,6 +288,40 @@ def test_textured_point_cloud_like_the_reference():
     assert (rb[pure] != ob[pure]).mean() <= 0.02
 
 
+def test_textured_fusion_on_reference_state():
+    """fuse_submaps with colours (fuse_with_interploation, dense_tsdf.py:273-280, colour line :276-277) EXECUTED on two
+    uniformly coloured submaps.  The oracle is given the reference's submap states as they are and fuses them: same voxel
+    set, same NaN pattern, fused colours (weight mixes of the two submap colours) within the f16 rounding of the
+    reference's sequential updates."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_texproj.npz"))
+    kw = dict(KW)
+    sub = OracleTSDF(is_global_map=False, mode=MODE_F16_FAITHFUL, **kw)
+    glo = OracleTSDF(is_global_map=True, mode=MODE_F16_FAITHFUL, **dict(kw, map_scale=[12.8, 12.8]))
+    for m in (sub, glo):
+        m.set_color(True, True)
+    for s in range(2):
+        for m in (sub, glo):
+            m.set_submap_pose(s, g["FU_base_R"][s], g["FU_base_T"][s])
+        idx = g[f"S{s}_idx"].astype(np.int32)
+        sub.scatter(s, idx, g[f"S{s}_T"].astype(np.float32), g[f"S{s}_W"].astype(np.float32), g[f"S{s}_occ"])
+        sub.scatter_color(s, idx, g[f"S{s}_color"].astype(np.float32))
+    glo.fuse_from(sub)
+    gi, gt, gw, go = glo.gather(0)
+    gc = glo.gather_color(0)
+    ri = g["FU_idx"].astype(np.int32)
+    assert set(map(tuple, ri)) == set(map(tuple, gi))
+    kg, kr = key_sort(gi), key_sort(ri)
+    rt, rw, rc = g["FU_T"].astype(np.float32)[kr], g["FU_W"].astype(np.float32)[kr], g["FU_color"].astype(np.float32)[kr]
+    fin = np.isfinite(rt) & np.isfinite(gt[kg]) & np.isfinite(rc).all(1) & np.isfinite(gc[kg]).all(1)
+    assert fin.mean() > 0.97
+    dc = np.abs(gc[kg][fin] - rc[fin])
+    # the reference accumulates colour and weight in f16 fields, one rounding per splatted corner
+    assert np.percentile(dc, 99) <= 1e-3 and dc.max() <= 3e-3, (np.percentile(dc, 99), dc.max())
+    A, B = g["colAB"].astype(np.float32) / 255.0
+    mixed = (np.abs(rc[fin] - A).max(1) > 2e-2) & (np.abs(rc[fin] - B).max(1) > 2e-2)
+    assert mixed.sum() > 1000   # voxels that really mix the two submaps' colours are compared
+
+
 def test_coloured_mesh_on_reference_state():
     """Coloured marching cubes (vertexInterp_color and its quirks, marching_cube_mesher.py:62-82, :104-108) EXECUTED on the
     banded-texture state of ref_exec_texproj.npz; the oracle meshes the same state (the reference's TSDF / W / colour

@@ -369,6 +369,38 @@ def texproj():
     g["P_idx"] = np.array([k[1:] for k in pkeys], np.int16)
     g["P_color"] = np.array([mp.color.d[k] for k in pkeys], np.float16)
     print(f"texproj: textured point cloud {len(pkeys)} voxels, {time.time() - t00:.0f}s")
+    # textured submaps fused into a global map (fuse_with_interploation :273-280 with the colour line :276-277): submap 0
+    # uniformly colour A, submap 1 colour B - the fused colour of a voxel is the weight mix of the two
+    from util import rot_xyz
+    sub = D(is_global_map=False, texture_enabled=True, **kw)
+    glo = D(is_global_map=True, texture_enabled=True, **dict(kw, map_scale=[12.8, 12.8]))
+    base = [(rot_xyz(0.1, 0.2, 0.3), np.array([0.5, 0.1, -0.2])), (rot_xyz(-0.3, 0.1, 1.0), np.array([-0.4, 0.6, 0.3]))]
+    dsmall = d1[::2, ::2].copy()
+    Ks = [v / 2 if i in (0, 2, 4, 5) else v for i, v in enumerate(K)]
+    sub.set_dep_camera_intrinsic(Ks)
+    colAB = np.array([(200, 40, 90), (10, 250, 30)], np.uint8)
+    for s_, (Rb, Tb) in enumerate(base):
+        sub.set_base_pose_submap(s_, Rb, Tb)
+        glo.set_base_pose_submap(s_, Rb, Tb)
+        Rw, Tw = Rb @ P1[0], Rb @ P1[1] + Tb
+        texs = np.zeros(dsmall.shape + (3,), np.uint8); texs[:] = colAB[s_]
+        sub.recast_depth_to_map(Rw, Tw, dsmall, texs)
+        skeys = sorted(k for k, v in sub.TSDF_observed.d.items() if v > 0 and k[0] == s_)
+        g[f"S{s_}_idx"] = np.array([k[1:] for k in skeys], np.int16)
+        g[f"S{s_}_T"] = np.array([sub.TSDF.d[k] for k in skeys], np.float16)
+        g[f"S{s_}_W"] = np.array([sub.W_TSDF.d[k] for k in skeys], np.float16)
+        g[f"S{s_}_occ"] = np.array([sub.occupy.d.get(k, 0) for k in skeys], np.int8)
+        g[f"S{s_}_color"] = np.array([sub.color.d[k] for k in skeys], np.float16)
+        if s_ == 0:
+            sub.switch_to_next_submap()
+    glo.fuse_submaps(sub)
+    gkeys = sorted(k for k, v in glo.TSDF_observed.d.items() if v > 0)
+    g["FU_idx"] = np.array([k[1:] for k in gkeys], np.int16)
+    g["FU_T"] = np.array([glo.TSDF.d[k] for k in gkeys], np.float16)
+    g["FU_W"] = np.array([glo.W_TSDF.d[k] for k in gkeys], np.float16)
+    g["FU_color"] = np.array([glo.color.d[k] for k in gkeys], np.float16)
+    g["FU_base_R"], g["FU_base_T"], g["colAB"] = np.stack([b[0] for b in base]), np.stack([b[1] for b in base]), colAB
+    print(f"texproj: textured fusion {len(gkeys)} voxels, {time.time() - t00:.0f}s")
     out = os.path.join(ROOT, "tests", "golden", "ref_exec_texproj.npz")
     np.savez_compressed(out, **g)
     c = g["color"].astype(np.float32)

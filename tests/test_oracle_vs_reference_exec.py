@@ -322,6 +322,25 @@ def test_textured_fusion_on_reference_state():
     assert mixed.sum() > 1000   # voxels that really mix the two submaps' colours are compared
 
 
+def test_textured_surface_export_on_reference_state():
+    """cvt_TSDF_surface_to_voxels of a TEXTURED map (dense_tsdf.py:339-362) executed: export_color is the voxel's colour
+    (not the jet value).  The oracle exports the same points with the same colours from the reference's state."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_exec_texproj.npz"))
+    fl, ce = [float(x) for x in g["surf_disp"]]
+    o = OracleTSDF(is_global_map=True, disp_floor=fl, disp_ceiling=ce, **KW)
+    o.set_color(True, False, list(g["Kc"]))
+    idx = g["idx"].astype(np.int32)
+    o.scatter(0, idx, g["T"].astype(np.float32), g["W"].astype(np.float32), g["occ"])
+    o.scatter_color(0, idx, g["color"].astype(np.float32))
+    ns, xyz, rgb = o.surface(0)
+    rx, rc = g["surf_xyz"], g["surf_color"]
+    assert ns == len(rx) > 1000
+    a_, b_ = np.lexsort(xyz.T[::-1]), np.lexsort(rx.T[::-1])
+    assert np.allclose(xyz[a_], rx[b_], atol=1e-6)
+    assert np.abs(rgb[a_] - rc[b_]).max() <= 1e-6   # (colours are f16 values on both sides)
+    assert len(np.unique(np.round(rc, 2), axis=0)) >= 3
+
+
 def test_coloured_mesh_on_reference_state():
     """Coloured marching cubes (vertexInterp_color and its quirks, marching_cube_mesher.py:62-82, :104-108) EXECUTED on the
     banded-texture state of ref_exec_texproj.npz; the oracle meshes the same state (the reference's TSDF / W / colour

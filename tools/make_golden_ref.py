@@ -338,7 +338,7 @@ def texproj():
     for x in range(tw):
         tex[:, x] = bands[x // 15]
     tex[0, 0] = (255, 255, 255)
-    m = D(is_global_map=True, texture_enabled=True, color_same_proj=False, **kw)
+    m = D(is_global_map=True, texture_enabled=True, color_same_proj=False, disp_floor=-3.0, disp_ceiling=3.0, **kw)  # (display range that keeps every voxel in the surface export)
     m.set_dep_camera_intrinsic(K)
     m.set_color_camera_intrinsic(Kc)
     m.set_base_pose_submap(0, np.eye(3), np.zeros(3))
@@ -356,6 +356,12 @@ def texproj():
     g["mc_vertices"] = mesher.mesh_vertices.to_numpy()[:3 * nt].astype(np.float32)
     g["mc_colors"] = mesher.mesh_colors.to_numpy()[:3 * nt].astype(np.float32)
     print(f"texproj: coloured mesh {nt} triangles, {time.time() - t00:.0f}s")
+    # surface export of a textured map (:339-362): export_color = the voxel's colour instead of the jet value
+    m.cvt_TSDF_surface_to_voxels()
+    ns = int(m.num_TSDF_particles[None])
+    g["surf_xyz"] = m.export_TSDF_xyz.to_numpy()[:ns].astype(np.float32)
+    g["surf_color"] = m.export_color.to_numpy()[:ns].astype(np.float32)
+    g["surf_disp"] = np.array([m.disp_floor, m.disp_ceiling])
     # textured point-cloud variant (:178-183): colour per point = one of 8 by the octant of its direction
     pal8 = np.array([(250, 20, 20), (20, 250, 20), (20, 20, 250), (240, 240, 30), (30, 240, 240), (240, 30, 240), (130, 130, 130),
                      (250, 140, 10)], np.uint8)
